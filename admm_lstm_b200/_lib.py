@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI in include/admm_lstm_b200.h (the stub INTEGRATION.md describes).
+
+The shared library is built in-tree by admm_lstm_b200/build.py.  There is deliberately no Python or
+CPU implementation behind these entry points: if the library is missing it is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libadmm_lstm_b200.so")
+
+ADMM_MAX_O = 16
+ADMM_MAX_CAND = 16
+ADMM_N_METRICS = 8
+VARIANT_ADMM, VARIANT_NO_DUAL_Y = 0, 1
+SRC_X, SRC_H = 0, 1
+
+fp = C.POINTER(C.c_float)
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+
+
+class Hyper(C.Structure):
+    _fields_ = [("rho", C.c_float * 7), ("beta_x", C.c_float * 4), ("beta_h", C.c_float * 4), ("beta_wy", C.c_float)]
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("n_global", C.c_int64), ("ldn", C.c_int64),
+        ("T", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("O", C.c_int32),
+        ("variant", C.c_int32), ("with_dual_y", C.c_int32),
+        ("hp", Hyper),
+        ("x", C.c_void_p), ("y", C.c_void_p),
+        ("gate", C.c_void_p * 6), ("dual", C.c_void_p * 5), ("dual_h", C.c_void_p),
+        ("a", C.c_void_p), ("dual_y", C.c_void_p),
+        ("wx", C.c_void_p), ("wh", C.c_void_p), ("wy", C.c_void_p),
+        ("tc_ws", C.c_void_p), ("tc_ws_bytes", C.c_int64),
+    ]
+
+
+PP = C.POINTER(Problem)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every function declared in include/admm_lstm_b200.h
+SIGNATURES = {
+    "admm_last_error": (C.c_char_p, []),
+    "admm_abi_version": (C.c_int, []),
+    "admm_sizeof_problem": (C.c_int, []),
+    "admm_device_ok": (C.c_int, []),
+    "admm_forward_t": (C.c_int, [PP, C.c_int, vp]),
+    "admm_predict": (C.c_int, [PP, vp, vp, vp]),
+    "admm_wy_grad": (C.c_int, [PP, vp, vp]),
+    "admm_wy_apply": (C.c_int, [PP, vp, vp]),
+    "admm_weight_grad": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "admm_weight_finish_grad": (C.c_int, [PP, C.c_int, vp, vp, vp]),
+    "admm_weight_probe": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]),
+    "admm_weight_select": (C.c_int, [PP, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "admm_weight_apply": (C.c_int, [PP, C.c_int, vp, vp, vp]),
+    "admm_sweep_t": (C.c_int, [PP, C.c_int, vp, vp]),
+    "admm_last_probe": (C.c_int, [PP, vp, vp]),
+    "admm_last_select": (C.c_int, [PP, vp, vp, vp]),
+    "admm_last_apply": (C.c_int, [PP, vp, vp, vp]),
+    "admm_tc_workspace_bytes": (C.c_int64, [PP]),
+    "admm_tc_refresh": (C.c_int, [PP, vp]),
+    "admm_launch_count": (C.c_int64, [C.c_int]),
+}
+
+_lib = None
+
+
+class AdmmLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libadmm_lstm_b200.so; raises (never falls back) when it is absent or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AdmmLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m admm_lstm_b200.build` (needs nvcc). "
+            "admm_lstm_b200 has no CPU/PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.admm_abi_version() != 1:
+        raise AdmmLibraryError("ABI version mismatch between _lib.py and the shared library")
+    if lib.admm_sizeof_problem() != C.sizeof(Problem):
+        raise AdmmLibraryError("admm_problem layout mismatch between _lib.py and the shared library")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().admm_last_error().decode("utf-8", "replace")
+        raise AdmmLibraryError(f"{what or 'admm call'} failed (code {rc}): {msg}")

@@ -1,0 +1,39 @@
+"""Sample-sharding plumbing: one process per GPU, torch.distributed for the few
+small all-reduces of a step (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class Comm:
+    """Thin view of the default process group; a no-op when the job has a single rank."""
+
+    def __init__(self, group=None):
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = group
+        self.world_size = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+
+    def allreduce_sum_(self, *tensors: torch.Tensor) -> None:
+        """In-place sum over ranks.  Identical reduced values on every rank keep the replicated
+        theta decisions (and therefore the weights) bit-identical without a broadcast."""
+        if not self.active:
+            return
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def shard_range(self, n_total: int) -> Tuple[int, int]:
+        """Contiguous, balanced slice [lo, hi) of n_total samples owned by this rank."""
+        base, rem = divmod(n_total, self.world_size)
+        lo = self.rank * base + min(self.rank, rem)
+        return lo, lo + base + (1 if self.rank < rem else 0)
+
+    def sum_int(self, value: int, device) -> int:
+        if not self.active:
+            return int(value)
+        t = torch.tensor([value], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())

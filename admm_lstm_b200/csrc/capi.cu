@@ -1,0 +1,255 @@
+// capi.cu -- the extern "C" surface declared in include/admm_lstm_b200.h.
+// Validates arguments, picks the kernel path (tcgen05 tensor-core path when a workspace is
+// attached and the shape is eligible, fp32 CUDA-core path otherwise) and launches.  There is no
+// CPU fallback: without an sm_100 device every compute entry point returns ADMM_ENODEV.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+#include "gate_gemm.h"
+#include "small_kernels.h"
+#include "tc_path.h"
+
+namespace admm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return ADMM_ECUDA;
+  }
+  return ADMM_OK;
+}
+
+static int device_ok() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return cached = 0;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return cached = 0;
+  return cached = (prop.major == 10) ? n : 0;
+}
+
+static int validate(const admm_problem* p, const char* who) {
+  if (!p) { set_error("%s: null problem", who); return ADMM_EINVAL; }
+  if (!device_ok()) { set_error("%s: no sm_100 CUDA device (this library has no CPU path)", who); return ADMM_ENODEV; }
+  ADMM_REQUIRE(p->n > 0 && p->n_global >= p->n, "%s: bad n=%lld n_global=%lld", who, (long long)p->n, (long long)p->n_global);
+  ADMM_REQUIRE(p->ldn >= p->n && p->ldn % 128 == 0, "%s: ldn=%lld must be a multiple of 128 and >= n", who, (long long)p->ldn);
+  ADMM_REQUIRE(p->T > 0 && p->D > 0 && p->H > 0 && p->O > 0, "%s: bad sizes T=%d D=%d H=%d O=%d", who, p->T, p->D, p->H, p->O);
+  ADMM_REQUIRE(p->O <= ADMM_MAX_O, "%s: output_size %d > %d", who, p->O, ADMM_MAX_O);
+  ADMM_REQUIRE(p->variant == ADMM_VARIANT_ADMM || p->variant == ADMM_VARIANT_NO_DUAL_Y, "%s: bad variant", who);
+  ADMM_REQUIRE(!(p->with_dual_y && p->variant == ADMM_VARIANT_NO_DUAL_Y), "%s: with_dual_y needs the admm variant", who);
+  return ADMM_OK;
+}
+
+static GateGemmArgs base_args(const admm_problem* p, int t_first) {
+  // t_first = first timestep t (1-based) of the launch
+  GateGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  const int64_t slab = (int64_t)p->H * p->ldn;
+  a.n = p->n; a.ldn = p->ldn; a.D = p->D; a.H = p->H;
+  a.x = p->x + (int64_t)(t_first - 1) * p->D * p->ldn;
+  a.h_prev = p->gate[5] + (int64_t)(t_first - 1) * slab;
+  a.c_prev = p->gate[4] + (int64_t)(t_first - 1) * slab;
+  a.x_tstride = (int64_t)p->D * p->ldn;
+  a.s_tstride = slab;
+  a.wx = p->wx; a.wh = p->wh;
+  for (int q = 0; q < 6; ++q) a.gate[q] = p->gate[q] + (int64_t)t_first * slab;
+  for (int q = 0; q < 5; ++q) a.dual[q] = p->dual[q] + (int64_t)t_first * slab;
+  a.dual_h = p->dual_h;
+  a.rho = make_rho(p->hp);
+  a.tc = 1;
+  a.tc_ws = p->tc_ws;
+  return a;
+}
+
+static int run_gate_gemm(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st) {
+  if (p->tc_ws && tc_eligible(p)) return gate_gemm_tc(mode, p, a, tc, st);
+  return gate_gemm_simt(mode, a, tc, st);
+}
+
+}  // namespace admm
+
+using namespace admm;
+
+extern "C" {
+
+const char* admm_last_error(void) { return g_err; }
+int admm_abi_version(void) { return ADMM_ABI_VERSION; }
+int admm_sizeof_problem(void) { return (int)sizeof(admm_problem); }
+int admm_device_ok(void) { return device_ok(); }
+int64_t admm_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int admm_forward_t(const admm_problem* p, int t, void* stream) {
+  int rc = validate(p, "admm_forward_t");
+  if (rc) return rc;
+  ADMM_REQUIRE(t >= 1 && t <= p->T, "admm_forward_t: t=%d out of 1..%d", t, p->T);
+  cudaStream_t st = (cudaStream_t)stream;
+  GateGemmArgs a = base_args(p, t);
+  rc = run_gate_gemm(GG_FORWARD, p, a, 1, st);
+  if (rc) return rc;
+  if (t == p->T && p->a)
+    return launch_output(p->gate[5] + (int64_t)p->T * p->H * p->ldn, p->wy, p->a, p->ldn, p->H, p->O, st);
+  return ADMM_OK;
+}
+
+int admm_predict(const admm_problem* p, float* work, float* out, void* stream) {
+  int rc = validate(p, "admm_predict");
+  if (rc) return rc;
+  ADMM_REQUIRE(work && out, "admm_predict: null buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t slab = (int64_t)p->H * p->ldn;
+  float* hbuf[2] = {work, work + slab};
+  float* cbuf[2] = {work + 2 * slab, work + 3 * slab};
+  if (cudaMemsetAsync(work, 0, sizeof(float) * 4 * slab, st) != cudaSuccess) return check_launch("predict memset");
+  for (int t = 1; t <= p->T; ++t) {
+    GateGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = p->n; a.ldn = p->ldn; a.D = p->D; a.H = p->H;
+    a.x = p->x + (int64_t)(t - 1) * p->D * p->ldn;
+    a.h_prev = hbuf[(t - 1) & 1];
+    a.c_prev = cbuf[(t - 1) & 1];
+    a.wx = p->wx; a.wh = p->wh;
+    a.gate[4] = cbuf[t & 1];
+    a.gate[5] = hbuf[t & 1];
+    a.rho = make_rho(p->hp);
+    a.tc = 1;
+    rc = gate_gemm_simt(GG_FORWARD, a, 1, st);
+    if (rc) return rc;
+  }
+  return launch_output(hbuf[p->T & 1], p->wy, out, p->ldn, p->H, p->O, st);
+}
+
+int admm_wy_grad(const admm_problem* p, double* g_acc, void* stream) {
+  int rc = validate(p, "admm_wy_grad");
+  if (rc) return rc;
+  ADMM_REQUIRE(g_acc, "admm_wy_grad: null accumulator");
+  return launch_wy_grad(*p, g_acc, (cudaStream_t)stream);
+}
+
+int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream) {
+  int rc = validate(p, "admm_wy_apply");
+  if (rc) return rc;
+  return launch_wy_apply(*p, g_acc, (cudaStream_t)stream);
+}
+
+int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scratch, double* g_acc,
+                     double* fw_acc, void* stream) {
+  int rc = validate(p, "admm_weight_grad");
+  if (rc) return rc;
+  ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_grad: bad src");
+  ADMM_REQUIRE(t0 >= 0 && tc >= 1 && t0 + tc <= p->T, "admm_weight_grad: bad timestep range %d+%d", t0, tc);
+  ADMM_REQUIRE(scratch && g_acc && fw_acc, "admm_weight_grad: null buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  GateGemmArgs a = base_args(p, t0 + 1);
+  a.scratch = scratch; a.tc = tc; a.fw_acc = fw_acc; a.src = src;
+  rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
+  if (rc) return rc;
+  AtrArgs r;
+  r.ldn = p->ldn; r.H = p->H; r.tc = tc;
+  r.K = (src == ADMM_SRC_X) ? p->D : p->H;
+  r.a_src = (src == ADMM_SRC_X) ? a.x : a.h_prev;
+  r.a_tstride = (int64_t)r.K * p->ldn;
+  r.scratch = scratch; r.g_acc = g_acc;
+  if (p->tc_ws && tc_eligible(p) && src == ADMM_SRC_H) return atr_tc(p, r, st);
+  return atr_simt(r, st);
+}
+
+int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out, void* stream) {
+  int rc = validate(p, "admm_weight_finish_grad");
+  if (rc) return rc;
+  rc = launch_weight_finish(*p, src, g_acc, grad_out, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (p->tc_ws && tc_eligible(p)) return tc_refresh_grad(p, src, grad_out, (cudaStream_t)stream);
+  return ADMM_OK;
+}
+
+int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, const float* grad, int k0, int ncand,
+                      const int32_t* done, double* fk_acc, void* stream) {
+  int rc = validate(p, "admm_weight_probe");
+  if (rc) return rc;
+  ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_probe: bad src");
+  ADMM_REQUIRE(t0 >= 0 && tc >= 1 && t0 + tc <= p->T, "admm_weight_probe: bad timestep range");
+  ADMM_REQUIRE(ncand >= 1 && ncand <= ADMM_MAX_CAND && k0 >= 0 && k0 + ncand <= 120, "admm_weight_probe: bad candidates");
+  GateGemmArgs a = base_args(p, t0 + 1);
+  a.tc = tc; a.src = src; a.grad = grad; a.k0 = k0; a.ncand = ncand; a.done = done; a.fk_acc = fk_acc;
+  return run_gate_gemm(GG_PROBE, p, a, tc, (cudaStream_t)stream);
+}
+
+int admm_weight_select(const admm_problem* p, int src, const float* grad, const double* fw_acc,
+                       const double* fk_acc, int k0, int ncand, int final_pass, int32_t* done, float* theta_out,
+                       void* stream) {
+  int rc = validate(p, "admm_weight_select");
+  if (rc) return rc;
+  ADMM_REQUIRE(ncand >= 1 && ncand <= ADMM_MAX_CAND, "admm_weight_select: bad ncand");
+  return launch_weight_select(*p, src, grad, fw_acc, fk_acc, k0, ncand, final_pass, done, theta_out,
+                              (cudaStream_t)stream);
+}
+
+int admm_weight_apply(const admm_problem* p, int src, const float* grad, const float* theta, void* stream) {
+  int rc = validate(p, "admm_weight_apply");
+  if (rc) return rc;
+  rc = launch_weight_apply(*p, src, grad, theta, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (p->tc_ws && tc_eligible(p)) return tc_refresh_weights(p, (cudaStream_t)stream);
+  return ADMM_OK;
+}
+
+int admm_sweep_t(const admm_problem* p, int t, double* metrics, void* stream) {
+  int rc = validate(p, "admm_sweep_t");
+  if (rc) return rc;
+  ADMM_REQUIRE(t >= 1 && t <= p->T, "admm_sweep_t: t=%d out of 1..%d", t, p->T);
+  GateGemmArgs a = base_args(p, t);
+  a.last = (t == p->T);
+  a.metrics = metrics;
+  return run_gate_gemm(GG_SWEEP, p, a, 1, (cudaStream_t)stream);
+}
+
+int admm_last_probe(const admm_problem* p, double* sums, void* stream) {
+  int rc = validate(p, "admm_last_probe");
+  if (rc) return rc;
+  return launch_last_probe(*p, sums, (cudaStream_t)stream);
+}
+int admm_last_select(const admm_problem* p, const double* sums, float* theta_out, void* stream) {
+  int rc = validate(p, "admm_last_select");
+  if (rc) return rc;
+  return launch_last_select(*p, sums, theta_out, (cudaStream_t)stream);
+}
+int admm_last_apply(const admm_problem* p, const float* theta, double* metrics, void* stream) {
+  int rc = validate(p, "admm_last_apply");
+  if (rc) return rc;
+  return launch_last_apply(*p, theta, metrics, (cudaStream_t)stream);
+}
+
+int64_t admm_tc_workspace_bytes(const admm_problem* p) {
+  if (!p) return 0;
+  return tc_workspace_bytes(p);
+}
+int admm_tc_refresh(const admm_problem* p, void* stream) {
+  int rc = validate(p, "admm_tc_refresh");
+  if (rc) return rc;
+  if (!(p->tc_ws && tc_eligible(p))) return ADMM_OK;
+  return tc_refresh_weights(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

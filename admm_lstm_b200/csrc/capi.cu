@@ -245,11 +245,29 @@ int64_t admm_tc_workspace_bytes(const admm_problem* p) {
   if (!p) return 0;
   return tc_workspace_bytes(p);
 }
-int admm_tc_refresh(const admm_problem* p, void* stream) {
+int admm_tc_refresh(const admm_problem* p, int what, void* stream) {
   int rc = validate(p, "admm_tc_refresh");
   if (rc) return rc;
   if (!(p->tc_ws && tc_eligible(p))) return ADMM_OK;
-  return tc_refresh_weights(p, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((what & ADMM_TC_WEIGHTS) && (rc = tc_refresh_weights(p, st))) return rc;
+  if ((what & ADMM_TC_INPUTS) && (rc = tc_refresh_inputs(p, st))) return rc;
+  if ((what & ADMM_TC_STATE) && (rc = tc_refresh_state(p, st))) return rc;
+  return ADMM_OK;
+}
+
+int admm_debug_preact(const admm_problem* p, int t, float* out, int use_tc, void* stream) {
+  int rc = validate(p, "admm_debug_preact");
+  if (rc) return rc;
+  ADMM_REQUIRE(t >= 1 && t <= p->T && out, "admm_debug_preact: bad arguments");
+  GateGemmArgs a = base_args(p, t);
+  a.scratch = out; a.tc = 1;
+  if (use_tc == 2) { a.dbg = out + 4LL * p->H * p->ldn; use_tc = 1; }
+  if (use_tc) {
+    ADMM_REQUIRE(p->tc_ws && tc_eligible(p), "admm_debug_preact: tensor-core path not available for this problem");
+    return gate_gemm_tc(GG_RAWZ, p, a, 1, (cudaStream_t)stream);
+  }
+  return gate_gemm_simt(GG_RAWZ, a, 1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

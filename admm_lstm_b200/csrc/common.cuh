@@ -28,6 +28,16 @@ __host__ __device__ inline Rho make_rho(const admm_hyper& hp) {
   return r;
 }
 
+// Low part of the 3xTF32 split.  The tensor core truncates the raw fp32 operand to tf32 itself (a_hi), so
+// a_lo = a - trunc_tf32(a) exactly; a_lo is then rounded to nearest tf32 here, because the MMA would
+// otherwise truncate it too and bias every product towards zero.
+__device__ __forceinline__ float tf32_round(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x00001000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float tf32_lo(float a) {
+  return tf32_round(a - __uint_as_float(__float_as_uint(a) & 0xFFFFE000u));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -7,7 +7,7 @@
 
 namespace admm {
 
-enum GateGemmMode { GG_FORWARD = 0, GG_SWEEP = 1, GG_GRAD = 2, GG_PROBE = 3 };
+enum GateGemmMode { GG_FORWARD = 0, GG_SWEEP = 1, GG_GRAD = 2, GG_PROBE = 3, GG_RAWZ = 7 /* debug: Z -> scratch */ };
 
 // All pointers are pre-offset to the first timestep of the launch (grid.z index tl = 0);
 // x_tstride / s_tstride are the element strides from one timestep slab to the next.
@@ -35,6 +35,8 @@ struct GateGemmArgs {
   const int32_t* done;   // PROBE: [4]
   double* fk_acc;        // PROBE: [4][NC] with NC = 8 if ncand <= 8 else ADMM_MAX_CAND
   void* tc_ws;           // tensor-core workspace or nullptr
+  float* dbg;            // debug dump buffer (RAWZ) or nullptr
+  float* h_lo;           // slab t of the h - tf32(h) side buffer (tensor-core path) or nullptr
 };
 
 int gate_gemm_simt(int mode, const GateGemmArgs& a, int tc, cudaStream_t st);

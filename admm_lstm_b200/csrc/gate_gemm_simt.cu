@@ -210,6 +210,15 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
 #pragma unroll
         for (int q = 0; q < 6; ++q)
           if (p.gate[q]) st_stream(p.gate[q] + off, make_float4(o_[q][0], o_[q][1], o_[q][2], o_[q][3]));
+        if (p.h_lo) st_stream(p.h_lo + off, make_float4(tf32_lo(o_[5][0]), tf32_lo(o_[5][1]), tf32_lo(o_[5][2]), tf32_lo(o_[5][3])));
+      }
+
+      if (MODE == GG_RAWZ) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float* dst = p.scratch + (((int64_t)g * H + j) * p.tc + tl) * ldn + n;
+          st_stream(dst, make_float4(acc[g][jj][v * 4 + 0], acc[g][jj][v * 4 + 1], acc[g][jj][v * 4 + 2], acc[g][jj][v * 4 + 3]));
+        }
       }
 
       if (MODE == GG_SWEEP) {
@@ -246,7 +255,10 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
 #pragma unroll
         for (int q = 0; q < 5; ++q)
           st_stream(p.gate[q] + off, make_float4(out_[q][0], out_[q][1], out_[q][2], out_[q][3]));
-        if (!p.last) st_stream(p.gate[5] + off, make_float4(out_[5][0], out_[5][1], out_[5][2], out_[5][3]));
+        if (!p.last) {
+          st_stream(p.gate[5] + off, make_float4(out_[5][0], out_[5][1], out_[5][2], out_[5][3]));
+          if (p.h_lo) st_stream(p.h_lo + off, make_float4(tf32_lo(out_[5][0]), tf32_lo(out_[5][1]), tf32_lo(out_[5][2]), tf32_lo(out_[5][3])));
+        }
 #pragma unroll
         for (int q = 0; q < 5; ++q)
           st_stream(p.dual[q] + off, make_float4(out_[6 + q][0], out_[6 + q][1], out_[6 + q][2], out_[6 + q][3]));
@@ -285,11 +297,11 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (!ok[e]) continue;
-            const float shift = lam[e] / rg + gv[e];
+            const float lr = lam[e] / rg;
             const float z0 = acc[g][jj][v * 4 + e], q = accq[g][jj][v * 4 + e];
 #pragma unroll
             for (int k = 0; k < NC; ++k)
-              if (k < p.ncand) msum[g * NC + k] += probe_point(z0, q, inv_theta[k], shift, g == 2);
+              if (k < p.ncand) msum[g * NC + k] += probe_point(z0, q, inv_theta[k], lr, gv[e], g == 2);
           }
         }
       }
@@ -329,6 +341,7 @@ int gate_gemm_simt(int mode, const GateGemmArgs& a, int tc, cudaStream_t st) {
     case GG_FORWARD: return small ? launch<GG_FORWARD, 4, 1>(a, tc, st) : launch<GG_FORWARD, 8, 1>(a, tc, st);
     case GG_SWEEP:   return small ? launch<GG_SWEEP, 4, 1>(a, tc, st) : launch<GG_SWEEP, 8, 1>(a, tc, st);
     case GG_GRAD:    return small ? launch<GG_GRAD, 4, 1>(a, tc, st) : launch<GG_GRAD, 8, 1>(a, tc, st);
+    case GG_RAWZ:    return launch<GG_RAWZ, 4, 1>(a, tc, st);
     case GG_PROBE:
       if (a.ncand <= 8) return launch<GG_PROBE, 4, 8>(a, tc, st);
       return launch<GG_PROBE, 4, ADMM_MAX_CAND>(a, tc, st);

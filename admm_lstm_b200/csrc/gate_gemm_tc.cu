@@ -1,0 +1,594 @@
+// gate_gemm_tc.cu -- tcgen05 / TMEM / TMA version of the "gate GEMM + fused epilogue" family (sm_100a).
+//
+//   Z[n, (g,j)] = sum_k x_t[k,n] W_g[k,j] + sum_k h_{t-1}[k,n] U_g[k,j]
+//
+// computed on the 5th-generation tensor cores as an fp32-accurate 3xTF32 product
+//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (a_hi = tf32 truncation done by the MMA itself,
+//                                                  a_lo = a - a_hi kept in a side buffer, b_hi/b_lo
+//                                                  pre-split copies of the small weight matrices)
+// because plain TF32 breaks the 1e-4 parity bar.
+//
+// Both operands are consumed in their native feature-major layout, i.e. MN-major for UMMA:
+//   A tile = 128 samples x BK features   (sample index contiguous in HBM)
+//   B tile = (4 gates x JC units) x BK   (unit index contiguous in HBM)
+// TMA (128B swizzle with 32B atoms, boxes of 32 floats x BK rows) lands them in the canonical MN-major layout, so
+// there is no transposed copy of the state or of the weights anywhere.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (one thread per sample row; TMEM lane == sample, TMEM column == (gate, unit)).
+// The accumulator never leaves the SM: the epilogue reads it with tcgen05.ld and applies the same
+// closed forms as the CUDA-core path (admm_math.cuh); all its global accesses are 128-byte warp rows.
+// Two CTAs are resident per SM (2 x 256 TMEM columns), so one tile's epilogue overlaps the other's MMAs.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "gate_gemm.h"
+#include "tc_path.h"
+
+namespace admm {
+namespace {
+
+constexpr int BM = 128;        // samples per tile (UMMA M)
+constexpr int BK = 16;         // features per pipeline stage (2 UMMA k-steps of 8)
+constexpr int NSTAGE = 2;
+constexpr int NTHREADS = 192;
+constexpr int CHUNK_BYTES = 32 * BK * 4;     // one TMA box: 32 floats (128 B) x BK rows
+
+struct TcMaps {
+  CUtensorMap x, x_lo, h, h_lo;         // dims (ldn, K, slabs)
+  CUtensorMap wx_hi, wx_lo, wh_hi, wh_lo;   // dims (H, K, 4)
+  CUtensorMap gx_hi, gx_lo;             // gradient of the probed weight, dims (H, Ksrc, 4)
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// MN-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
+// For 32-bit (tf32) MN-major operands the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (=1):
+// rows of 128 B (32 samples/units) per k, 32-byte units XOR-swizzled with (k mod 4); plain SWIZZLE_128B reads
+// as zeros (measured, scripts/tc_micro.cu).  TMA writes exactly this with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// LBO = byte stride between 32-element chunks along MN, SBO = byte stride between 4-row groups along K.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((uint32_t)(CHUNK_BYTES) >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, A MN-major [15],
+// B MN-major [16], N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+template <int MODE>
+struct Cfg {
+  static constexpr bool PROBE = (MODE == GG_PROBE);
+  static constexpr int JC = PROBE ? 32 : 64;          // hidden units per tile
+  static constexpr int NCOL = 4 * JC;                 // accumulator columns of Z
+  static constexpr int TMEM_COLS = 256;               // Z (+ Q for PROBE)
+  static constexpr int A_BYTES = BM * BK * 4;         // 8 KB
+  static constexpr int B_BYTES = NCOL * BK * 4;       // 16 KB (8 KB for PROBE)
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES + (PROBE ? 2 * B_BYTES : 0);
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
+};
+
+
+template <int MODE, int NC>
+__global__ void __launch_bounds__(NTHREADS, 2)
+gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0) {
+  using C = Cfg<MODE>;
+  constexpr int JC = C::JC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[4 * ADMM_MAX_CAND * 4];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BM;
+  const int j0 = blockIdx.y * JC;
+  const int tl = blockIdx.z;
+  const int D = p.D, H = p.H;
+  const int nkx = (D + BK - 1) / BK, nkh = (H + BK - 1) / BK, nkb = nkx + nkh;
+
+  if (MODE == GG_PROBE) {
+    if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int q_lo = (MODE == GG_PROBE) ? (p.src == ADMM_SRC_X ? 0 : nkx) : 0;
+  const int q_hi = (MODE == GG_PROBE) ? (p.src == ADMM_SRC_X ? nkx : nkb) : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NSTAGE, it = kb / NSTAGE;
+        if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
+        const bool is_x = kb < nkx;
+        const int k0 = (is_x ? kb : kb - nkx) * BK;
+        const bool qk = (MODE == GG_PROBE) && kb >= q_lo && kb < q_hi;
+        uint8_t* st = smem + s * C::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES + (qk ? 2 * C::B_BYTES : 0));
+        const CUtensorMap* ma = is_x ? &maps.x : &maps.h;
+        const CUtensorMap* ml = is_x ? &maps.x_lo : &maps.h_lo;
+        const int slab = slab0 + tl;
+#pragma unroll
+        for (int c = 0; c < BM / 32; ++c) {
+          tma_load_3d(st + c * CHUNK_BYTES, ma, &full_bar[s], n0 + 32 * c, k0, slab);
+          tma_load_3d(st + C::A_BYTES + c * CHUNK_BYTES, ml, &full_bar[s], n0 + 32 * c, k0, slab);
+        }
+        const CUtensorMap* bh = is_x ? &maps.wx_hi : &maps.wh_hi;
+        const CUtensorMap* bl = is_x ? &maps.wx_lo : &maps.wh_lo;
+        uint8_t* sb = st + 2 * C::A_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int c = 0; c < JC / 32; ++c) {
+            const int chunk = g * (JC / 32) + c;
+            tma_load_3d(sb + chunk * CHUNK_BYTES, bh, &full_bar[s], j0 + 32 * c, k0, g);
+            tma_load_3d(sb + C::B_BYTES + chunk * CHUNK_BYTES, bl, &full_bar[s], j0 + 32 * c, k0, g);
+          }
+        if (qk) {
+          uint8_t* sg = sb + 2 * C::B_BYTES;
+          const int kq = (kb - q_lo) * BK;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int c = 0; c < JC / 32; ++c) {
+              const int chunk = g * (JC / 32) + c;
+              tma_load_3d(sg + chunk * CHUNK_BYTES, &maps.gx_hi, &full_bar[s], j0 + 32 * c, kq, g);
+              tma_load_3d(sg + C::B_BYTES + chunk * CHUNK_BYTES, &maps.gx_lo, &full_bar[s], j0 + 32 * c, kq, g);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, C::NCOL);
+      bool first_q = true;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NSTAGE, it = kb / NSTAGE;
+        mbar_wait(&full_bar[s], it & 1);
+        tc_fence_after();
+        const bool qk = (MODE == GG_PROBE) && kb >= q_lo && kb < q_hi;
+        const uint32_t st = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + C::A_BYTES;
+        const uint32_t b_hi = st + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t off = ks * 1024;
+          const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
+          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc0);
+          umma_tf32(tmem_base, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
+          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
+          if (qk) {
+            const uint32_t g_hi = b_hi + 2 * C::B_BYTES, g_lo = g_hi + C::B_BYTES;
+            const uint32_t accq = (first_q && ks == 0) ? 0u : 1u;
+            umma_tf32(tmem_base + C::NCOL, make_desc(a_hi + off), make_desc(g_hi + off), idesc, accq);
+            umma_tf32(tmem_base + C::NCOL, make_desc(a_lo + off), make_desc(g_hi + off), idesc, 1u);
+            umma_tf32(tmem_base + C::NCOL, make_desc(a_hi + off), make_desc(g_lo + off), idesc, 1u);
+          }
+        }
+        if (qk) first_q = false;
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+    const int row = quarter * 32 + lane;
+    const int64_t n = (int64_t)n0 + row;
+    const bool ok = n < p.n;
+    const int64_t ldn = p.ldn;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const Rho rho = p.rho;
+    const int64_t soff = (int64_t)tl * p.s_tstride;
+    constexpr int NM = (MODE == GG_PROBE) ? 4 * NC : 4;
+    float msum[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) msum[k] = 0.f;
+    int done_g[4] = {0, 0, 0, 0};
+    if (MODE == GG_PROBE) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) done_g[g] = p.done[g];
+    }
+
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    if (MODE == GG_RAWZ && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      const int et = threadIdx.x - 64;
+      const float* sf = reinterpret_cast<const float*>(smem);
+      for (int i = et; i < NSTAGE * C::STAGE_BYTES / 4; i += 128) p.dbg[i] = sf[i];
+      float* td = p.dbg + NSTAGE * C::STAGE_BYTES / 4;
+      for (int cb = 0; cb < 256; cb += 8) {
+        float v[8];
+        tmem_ld8(t_row + cb, v);
+        for (int e = 0; e < 8; ++e) td[row * 256 + cb + e] = v[e];
+      }
+      if (et == 0) { td[128 * 256] = __uint_as_float(tmem_base); }
+    }
+
+    for (int jb = 0; jb < JC; jb += 8) {
+      float z[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld8(t_row + g * JC + jb, z[g]);
+      float q[(MODE == GG_PROBE) ? 4 : 1][8];
+      if (MODE == GG_PROBE) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld8(t_row + C::NCOL + g * JC + jb, q[g]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = j0 + jb + e;
+        const int64_t off = soff + (int64_t)j * ldn + n;
+        if (MODE == GG_RAWZ) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            p.scratch[(((int64_t)g * H + j) * p.tc + tl) * ldn + n] = z[g][e];
+        }
+        if (MODE == GG_FORWARD) {
+          const ForwardResult r = forward_point(z[0][e], z[1][e], z[2][e], z[3][e], p.c_prev[off]);
+          if (p.gate[0]) p.gate[0][off] = r.i;
+          if (p.gate[1]) p.gate[1][off] = r.f;
+          if (p.gate[2]) p.gate[2][off] = r.g;
+          if (p.gate[3]) p.gate[3][off] = r.o;
+          p.gate[4][off] = r.c;
+          p.gate[5][off] = r.h;
+          if (p.h_lo) p.h_lo[off] = tf32_lo(r.h);
+        }
+        if (MODE == GG_SWEEP) {
+          SweepPoint s;
+          s.zi = z[0][e]; s.zf = z[1][e]; s.zg = z[2][e]; s.zo = z[3][e];
+          s.i = p.gate[0][off]; s.f = p.gate[1][off]; s.g = p.gate[2][off]; s.o = p.gate[3][off];
+          s.c = p.gate[4][off]; s.h = p.gate[5][off]; s.c_prev = p.c_prev[off];
+          s.li = p.dual[0][off]; s.lf = p.dual[1][off]; s.lg = p.dual[2][off]; s.lo = p.dual[3][off];
+          s.lc = p.dual[4][off];
+          s.lh = p.last ? p.dual_h[(int64_t)j * ldn + n] : 0.f;
+          const SweepResult r = sweep_point(s, rho, p.last != 0);
+          p.gate[0][off] = r.i; p.gate[1][off] = r.f; p.gate[2][off] = r.g; p.gate[3][off] = r.o;
+          p.gate[4][off] = r.c;
+          if (!p.last) {
+            p.gate[5][off] = r.h;
+            if (p.h_lo) p.h_lo[off] = tf32_lo(r.h);
+          }
+          p.dual[0][off] = r.li; p.dual[1][off] = r.lf; p.dual[2][off] = r.lg; p.dual[3][off] = r.lo;
+          p.dual[4][off] = r.lc;
+          if (ok) { msum[0] += r.prim_sq; msum[1] += r.dual_sq; msum[2] += r.penalty; }
+        }
+        if (MODE == GG_GRAD) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float rg = (g == 0) ? rho.i : (g == 1) ? rho.f : (g == 2) ? rho.g : rho.o;
+            float u;
+            const float rr = grad_point(z[g][e], p.dual[g][off], p.gate[g][off], rg, g == 2, &u);
+            p.scratch[(((int64_t)g * H + j) * p.tc + tl) * ldn + n] = ok ? rr : 0.f;
+            if (ok) msum[g] += u * u;
+          }
+        }
+        if (MODE == GG_PROBE) {
+          if (ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (done_g[g]) continue;
+              const float rg = (g == 0) ? rho.i : (g == 1) ? rho.f : (g == 2) ? rho.g : rho.o;
+              const float lr = p.dual[g][off] / rg, gv = p.gate[g][off];
+#pragma unroll
+              for (int k = 0; k < NC; ++k)
+                if (k < p.ncand)
+                  msum[g * NC + k] += probe_point(z[g][e], q[g][e], ldexpf(1.0f, -(p.k0 + k)), lr, gv, g == 2);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    // block-level reduction of the metric partials over the 4 epilogue warps
+    if (MODE == GG_SWEEP || MODE == GG_GRAD || MODE == GG_PROBE) {
+      double* dst = (MODE == GG_SWEEP) ? p.metrics : (MODE == GG_GRAD) ? p.fw_acc : p.fk_acc;
+      constexpr int NOUT = (MODE == GG_SWEEP) ? 3 : NM;
+      if (dst) {
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+          const float s = warp_sum(msum[k]);
+          if (lane == 0) red[k * 4 + quarter] = s;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = threadIdx.x - 64;
+        if (et < NOUT) {
+          const double s = (double)red[et * 4 + 0] + (double)red[et * 4 + 1] + (double)red[et * 4 + 2] +
+                           (double)red[et * 4 + 3];
+          atomicAdd(dst + et, s);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)ptr;
+  }
+  return fn;
+}
+
+// 3-D fp32 tensor [d2][d1][d0] (d0 contiguous), box 32 x BK x 1, SWIZZLE_128B_ATOM_32B, zero fill out of bounds.
+int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+             uint64_t stride2_elems) {
+  EncodeFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADMM_ECUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 4, stride2_elems * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)BK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return ADMM_ECUDA; }
+  return ADMM_OK;
+}
+
+// workspace layout (floats): [x_lo T*D*ldn][h_lo (T+1)*H*ldn][wx_hi 4DH][wx_lo 4DH][wh_hi 4HH][wh_lo 4HH][g_hi 4KmaxH][g_lo 4KmaxH]
+struct WsLayout {
+  int64_t x_lo, h_lo, wx_hi, wx_lo, wh_hi, wh_lo, g_hi, g_lo, total;
+};
+WsLayout ws_layout(const admm_problem* p) {
+  WsLayout w;
+  const int64_t T = p->T, D = p->D, H = p->H, ldn = p->ldn;
+  const int64_t kmax = D > H ? D : H;
+  int64_t o = 0;
+  auto take = [&](int64_t n) { const int64_t r = o; o += (n + 255) / 256 * 256; return r; };
+  w.x_lo = take(T * D * ldn);
+  w.h_lo = take((T + 1) * H * ldn);
+  w.wx_hi = take(4 * D * H); w.wx_lo = take(4 * D * H);
+  w.wh_hi = take(4 * H * H); w.wh_lo = take(4 * H * H);
+  w.g_hi = take(4 * kmax * H); w.g_lo = take(4 * kmax * H);
+  w.total = o;
+  return w;
+}
+
+__global__ void split_trunc_kernel(const float* __restrict__ src, float* __restrict__ lo, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    float4 r;
+    r.x = tf32_lo(v.x); r.y = tf32_lo(v.y); r.z = tf32_lo(v.z); r.w = tf32_lo(v.w);
+    *reinterpret_cast<float4*>(lo + i) = r;
+  } else {
+    for (int64_t k = i; k < n; ++k) lo[k] = tf32_lo(src[k]);
+  }
+}
+// weights: hi = round-to-nearest tf32 (the MMA then truncates an already-representable value), lo = w - hi
+__global__ void split_round_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  const float h = tf32_round(v);
+  hi[i] = h;
+  lo[i] = tf32_round(v - h);
+}
+
+struct MapKey {
+  const void *x, *h, *ws;
+  int64_t ldn;
+  int T, D, H;
+  bool operator<(const MapKey& o) const {
+    return std::tie(x, h, ws, ldn, T, D, H) < std::tie(o.x, o.h, o.ws, o.ldn, o.T, o.D, o.H);
+  }
+};
+std::mutex g_map_mu;
+std::map<MapKey, TcMaps> g_maps;
+
+int get_maps(const admm_problem* p, int src, TcMaps* out) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  const MapKey key{p->x, p->gate[5], p->tc_ws, p->ldn, p->T, p->D, p->H};
+  auto it = g_maps.find(key);
+  if (it == g_maps.end()) {
+    if (g_maps.size() > 64) g_maps.clear();
+    TcMaps m;
+    float* ws = (float*)p->tc_ws;
+    const WsLayout w = ws_layout(p);
+    const uint64_t ldn = p->ldn, T = p->T, D = p->D, H = p->H;
+    int rc = 0;
+    rc |= make_map(&m.x, p->x, ldn, D, T, ldn, D * ldn);
+    rc |= make_map(&m.x_lo, ws + w.x_lo, ldn, D, T, ldn, D * ldn);
+    rc |= make_map(&m.h, p->gate[5], ldn, H, T + 1, ldn, H * ldn);
+    rc |= make_map(&m.h_lo, ws + w.h_lo, ldn, H, T + 1, ldn, H * ldn);
+    rc |= make_map(&m.wx_hi, ws + w.wx_hi, H, D, 4, H, D * H);
+    rc |= make_map(&m.wx_lo, ws + w.wx_lo, H, D, 4, H, D * H);
+    rc |= make_map(&m.wh_hi, ws + w.wh_hi, H, H, 4, H, H * H);
+    rc |= make_map(&m.wh_lo, ws + w.wh_lo, H, H, 4, H, H * H);
+    if (rc) return ADMM_ECUDA;
+    it = g_maps.emplace(key, m).first;
+  }
+  *out = it->second;
+  // the gradient maps depend on src (K = D or H); they are cheap to encode per call
+  const WsLayout w = ws_layout(p);
+  float* ws = (float*)p->tc_ws;
+  const uint64_t K = (src == ADMM_SRC_X) ? p->D : p->H, H = p->H;
+  int rc = make_map(&out->gx_hi, ws + w.g_hi, H, K, 4, H, K * H);
+  rc |= make_map(&out->gx_lo, ws + w.g_lo, H, K, 4, H, K * H);
+  return rc ? ADMM_ECUDA : ADMM_OK;
+}
+
+template <int MODE, int NC>
+int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, int slab0, int tc, cudaStream_t st) {
+  using C = Cfg<MODE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gate_gemm_tc_kernel<MODE, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    configured = true;
+  }
+  dim3 grid((unsigned)(p->ldn / BM), (unsigned)(p->H / C::JC), (unsigned)tc);
+  gate_gemm_tc_kernel<MODE, NC><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a, maps, slab0);
+  count_launch();
+  return check_launch("gate_gemm_tc");
+}
+
+}  // namespace
+
+bool tc_eligible(const admm_problem* p) {
+  return p->H % 64 == 0 && p->H >= 64 && p->ldn % 128 == 0 && get_encode() != nullptr;
+}
+
+int64_t tc_workspace_bytes(const admm_problem* p) {
+  if (!(p->H % 64 == 0 && p->H >= 64 && p->ldn % 128 == 0)) return 0;
+  return ws_layout(p).total * 4;
+}
+
+int tc_refresh_weights(const admm_problem* p, cudaStream_t st) {
+  const WsLayout w = ws_layout(p);
+  float* ws = (float*)p->tc_ws;
+  const int64_t nx = 4LL * p->D * p->H, nh = 4LL * p->H * p->H;
+  split_round_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(p->wx, ws + w.wx_hi, ws + w.wx_lo, nx);
+  split_round_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(p->wh, ws + w.wh_hi, ws + w.wh_lo, nh);
+  count_launch(2);
+  return check_launch("tc_refresh_weights");
+}
+
+int tc_refresh_inputs(const admm_problem* p, cudaStream_t st) {
+  const WsLayout w = ws_layout(p);
+  float* ws = (float*)p->tc_ws;
+  const int64_t nx = (int64_t)p->T * p->D * p->ldn;
+  split_trunc_kernel<<<(unsigned)((nx / 4 + 255) / 256 + 1), 256, 0, st>>>(p->x, ws + w.x_lo, nx);
+  count_launch();
+  return check_launch("tc_refresh_inputs");
+}
+
+int tc_refresh_state(const admm_problem* p, cudaStream_t st) {
+  const WsLayout w = ws_layout(p);
+  float* ws = (float*)p->tc_ws;
+  const int64_t nh = (int64_t)(p->T + 1) * p->H * p->ldn;
+  split_trunc_kernel<<<(unsigned)((nh / 4 + 255) / 256 + 1), 256, 0, st>>>(p->gate[5], ws + w.h_lo, nh);
+  count_launch();
+  return check_launch("tc_refresh_state");
+}
+
+int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStream_t st) {
+  const WsLayout w = ws_layout(p);
+  float* ws = (float*)p->tc_ws;
+  const int64_t n = 4LL * (src == ADMM_SRC_X ? p->D : p->H) * p->H;
+  split_round_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad, ws + w.g_hi, ws + w.g_lo, n);
+  count_launch();
+  return check_launch("tc_refresh_grad");
+}
+
+float* tc_h_lo(const admm_problem* p) {
+  return (float*)p->tc_ws + ws_layout(p).h_lo;
+}
+
+int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int tc, cudaStream_t st) {
+  GateGemmArgs a = a_in;
+  TcMaps maps;
+  int rc = get_maps(p, a.src, &maps);
+  if (rc) return rc;
+  // slab index of h_{t-1} / x_t of the first timestep in the launch
+  const int64_t slab_elems = (int64_t)p->H * p->ldn;
+  const int slab0 = (int)((a.h_prev - p->gate[5]) / slab_elems);
+  a.h_lo = tc_h_lo(p) + (a.gate[5] - p->gate[5]);
+  switch (mode) {
+    case GG_FORWARD: return launch_tc<GG_FORWARD, 1>(p, a, maps, slab0, tc, st);
+    case GG_SWEEP: return launch_tc<GG_SWEEP, 1>(p, a, maps, slab0, tc, st);
+    case GG_GRAD: return launch_tc<GG_GRAD, 1>(p, a, maps, slab0, tc, st);
+    case GG_PROBE:
+      if (a.ncand <= 8) return launch_tc<GG_PROBE, 8>(p, a, maps, slab0, tc, st);
+      return launch_tc<GG_PROBE, ADMM_MAX_CAND>(p, a, maps, slab0, tc, st);
+    case GG_RAWZ: return launch_tc<GG_RAWZ, 1>(p, a, maps, slab0, tc, st);
+  }
+  set_error("gate_gemm_tc: bad mode %d", mode);
+  return ADMM_EINVAL;
+}
+
+int atr_tc(const admm_problem*, const AtrArgs& a, cudaStream_t st) { return atr_simt(a, st); }
+
+}  // namespace admm

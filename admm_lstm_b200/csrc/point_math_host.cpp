@@ -30,6 +30,6 @@ void admm_host_grad_points(const float* z, const float* lam, const float* gate, 
 void admm_host_probe_points(const float* z0, const float* q, float inv_theta, const float* lam, const float* gate,
                             float rho, int is_g, float* out, long n) {
   for (long e = 0; e < n; ++e)
-    out[e] = admm::probe_point(z0[e], q[e], inv_theta, lam[e] / rho + gate[e], is_g != 0);
+    out[e] = admm::probe_point(z0[e], q[e], inv_theta, lam[e] / rho, gate[e], is_g != 0);
 }
 }

@@ -199,7 +199,7 @@ class ADMMBasedOptimizer(object):
         if want_tc:
             self._tc_ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
             p.tc_ws, p.tc_ws_bytes = self._tc_ws.data_ptr(), ws_bytes
-            self._call("admm_tc_refresh", self._pp, _stream_ptr())
+            self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS | _lib.TC_INPUTS, _stream_ptr())
         self.uses_tensor_cores = want_tc
 
         self.gates = _StateDict({**{k: (lambda k=k: self._state[k].permute(2, 0, 1)[:N]) for k in _STATE_KEYS},
@@ -294,7 +294,7 @@ class ADMMBasedOptimizer(object):
                 self._pull_weights_from_model()
                 self._bind_weights_to_model()
                 if self._tc_ws is not None:
-                    self._call("admm_tc_refresh", self._pp, _stream_ptr())
+                    self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS, _stream_ptr())
                 return
 
     # ------------------------------------------------------------------------------------ plumbing
@@ -331,6 +331,13 @@ class ADMMBasedOptimizer(object):
         yd = train_y.to(self.device, non_blocking=True)
         self._x[:, :, :n].copy_(xd.permute(1, 2, 0))
         self._y[:, :n].copy_(yd.t())
+        if self._tc_ws is not None:
+            self._call("admm_tc_refresh", self._pp, _lib.TC_INPUTS, _stream_ptr())
+
+    def state_changed(self) -> None:
+        """Call after writing the state buffers directly (tests do): re-derives the tensor-core side buffers."""
+        if self._tc_ws is not None:
+            self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS | _lib.TC_STATE, _stream_ptr())
 
     def export_weights(self, out: Dict[str, torch.Tensor]) -> None:
         """Device->host read of the step's result (the nine weight tensors) into pinned buffers."""

@@ -74,7 +74,8 @@ typedef struct admm_problem {
   float* wh;       /* [4][H][H]       */
   float* wy;       /* [H][O]          */
   /* Optional operands of the tensor-core path (NULL -> fp32 CUDA-core path), see
-   * admm_tc_workspace_bytes(): TF32 hi/lo splits kept by the library. */
+   * admm_tc_workspace_bytes(): TF32 hi/lo splits kept by the library.  Must be zero-filled once
+   * by the caller before first use. */
   void* tc_ws;
   int64_t tc_ws_bytes;
 } admm_problem;
@@ -150,8 +151,15 @@ int admm_last_apply(const admm_problem* p, const float* theta, double* metrics, 
 /* Tensor-core (tcgen05 / TMA, 3xTF32) path for the gate GEMMs.  Returns 0 bytes when the shape is
  * not eligible (H % 64, ldn % 128, ...); otherwise the workspace the caller must provide in
  * admm_problem.tc_ws.  admm_tc_refresh() re-splits the weights after they change. */
+#define ADMM_TC_WEIGHTS 1 /* wx, wh changed outside admm_weight_apply     */
+#define ADMM_TC_INPUTS 2  /* x changed                                      */
+#define ADMM_TC_STATE 4   /* h changed outside admm_forward_t / admm_sweep_t */
 int64_t admm_tc_workspace_bytes(const admm_problem* p);
-int admm_tc_refresh(const admm_problem* p, void* stream);
+int admm_tc_refresh(const admm_problem* p, int what, void* stream);
+
+/* Test hook: out[4][H][ldn] = pre-activations z_g = x_t W_g + h_{t-1} U_g at timestep t, through the
+ * tensor-core path (use_tc != 0, needs tc_ws) or the CUDA-core path. */
+int admm_debug_preact(const admm_problem* p, int t, float* out, int use_tc, void* stream);
 
 /* Launch counter: number of kernels this library has launched since the last reset
  * (bench.py reports it as gpu_launches). */

@@ -116,6 +116,11 @@ class OracleADMM:
             self.duals = {k: np.array(v, dtype=F32) for k, v in state["duals"].items()}
         self.trace = {}        # theta decisions of the last step, for diagnostics only
         self.f_evals = 0       # number of full-data original_func evaluations (cost model)
+        # Test hooks for knife-edge backtracking decisions: `forced` maps a weight name
+        # (or 'h_T') to the theta to apply instead of the one the loop finds; `margins` records, per name,
+        # (theta, f(beta), est, f(w)) of every comparison the loop made.
+        self.forced = {}
+        self.margins = {}
 
     # ---- reductions that couple samples -------------------------------------------------
     def _sum(self, v):
@@ -218,13 +223,22 @@ class OracleADMM:
 
         theta = 1
         beta = w + gradient / F32(theta)
-        while original_func(beta) > estimated_func(beta, theta):      # admm.py:334
+        name = f"{src}2{gate}"
+        self.margins[name] = []
+
+        def keep_going(beta_t, theta_t):
+            fb, est = original_func(beta_t), estimated_func(beta_t, theta_t)
+            self.margins[name].append((float(theta_t), float(fb), float(est)))
+            return fb > est
+
+        while keep_going(beta, theta):                                # admm.py:334
             theta *= 2
             beta = w + gradient / F32(theta)
             if theta > 2.0 ** 60:         # the reference has no cap; a NaN exits its loop anyway
                 break
         theta /= 2
-        self.trace[f"{src}2{gate}"] = theta
+        self.trace[name] = theta
+        theta = self.forced.get(name, theta)
         tau = F32(0.5) * rho * F32(T) * F32(theta)                    # admm.py:341 left-to-right
         self.w[f"{src}2{gate}"] = ((tau * w - gradient) /
                                    (self.betas[f"{src}2{gate}"] + F32(0.5) * rho * F32(theta) * F32(T))).astype(F32)
@@ -317,6 +331,7 @@ class OracleADMM:
                 break
         theta /= 2
         self.trace["h_T"] = theta
+        theta = self.forced.get("h_T", theta)
         g["h"][:, t, :] = compute_h(theta)                              # admm.py:482-487
 
     def update_primal_a(self):

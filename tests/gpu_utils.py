@@ -36,6 +36,7 @@ def load_state(opt, state):
     opt._dual_h[:, :n] = torch.from_numpy(state["duals"]["h"][:, T, :]).to(dev).t()
     opt._a[:, :n] = torch.from_numpy(state["gates"]["a"]).to(dev).t()
     opt._dual_y[:, :n] = torch.from_numpy(state["duals"]["y"]).to(dev).t()
+    opt.state_changed()
 
 
 def weights_of(opt):

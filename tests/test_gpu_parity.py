@@ -44,6 +44,10 @@ def test_per_function_vs_reference_fixture(variant):
     base_w = {k: rec[f"base_w_{k}"] for k in WKEYS}
     st = state_from(rec, "base_")
     tt, T = int(rec["tt"]), rec["x"].shape[1]
+    # invariant of every real run (admm.py:533-534): lambda_h is zero for t < T; the device layout
+    # stores only the t = T slot, so the sweep comparison starts from a state that honours it.
+    st["duals"]["h"] = st["duals"]["h"].copy()
+    st["duals"]["h"][:, :T, :] = 0
 
     def fresh():
         model, opt = make_opt(base_w, rec["x"], rec["y"], GOOGLE, variant)
@@ -92,7 +96,8 @@ def test_per_function_vs_reference_fixture(variant):
     s = torch.cuda.current_stream().cuda_stream
     opt._call("admm_sweep_t", opt._pp, tt, 0, s)
     gates, _ = np_state(opt)
-    np.testing.assert_allclose(gates["i"][:, tt], rec["fn_primal_i"], rtol=2e-5, atol=2e-6)   # i is updated first
+    # i is updated first and does not involve lambda_h: directly comparable with the reference's own output
+    np.testing.assert_allclose(gates["i"][:, tt], rec["fn_primal_i"], rtol=2e-5, atol=2e-6)
 
 
 @pytest.mark.parametrize("name,variant,params,dualy", [
@@ -132,8 +137,16 @@ def test_trajectory_vs_reference_fixture(name, variant, params, dualy):
     ("googlestock", "admm", GOOGLE), ("googlestock", "no_dual_y", GOOGLE),
     ("gefcom_standin", "admm", GEFCOM), ("gefcom_standin", "no_dual_y", GEFCOM_FAST),
 ])
-def test_real_data_50_iterations(dataset, variant, params):
-    """BASELINE.json configs 1-2: 50 iterations, weights per iteration, loss curves, snapshots."""
+def test_real_data_50_iterations_vs_reference_curves(dataset, variant, params):
+    """BASELINE.json configs 1-2 against the golden curves of the unmodified reference: 50 iterations,
+    weights, loss curves and state snapshots.
+
+    Tolerance note: on GoogleStock the x2g backtracking sits on a knife edge in EVERY
+    iteration (D = 1 and sum x^2 / T is ~2^8, so f(beta)-est at the deciding theta is ~1e-8 against terms of
+    1e-3); which side it falls on depends on the last bit of tanh.  A flipped theta is an equally valid ADMM
+    iterate that moves the weights by ~1e-4..1e-3 for the rest of the run (measured by forcing one flip in
+    the oracle).  So: weights/loss must match to 1e-4 until the first flip and to 2e-3 after it, the final
+    losses to 1 %; the companion test below pins the arithmetic to 1e-4 with the decisions synchronised."""
     _need_gpu()
     from gpu_utils import make_opt, np_state, weights_of
     data = load(f"{dataset}_data.npz")
@@ -141,20 +154,22 @@ def test_real_data_50_iterations(dataset, variant, params):
     model, opt = make_opt(weights_from(rec, "init_"), data["train_x"], data["train_y"], params, variant)
     tx, ty = torch.from_numpy(data["train_x"]).cuda(), torch.from_numpy(data["train_y"]).cuda()
     vx, vy = torch.from_numpy(data["val_x"]).cuda(), torch.from_numpy(data["val_y"]).cuda()
-    worst = 0.0
+    worst, first_flip = 0.0, None
     for it in range(1, 51):
         opt.step()
         w = weights_of(opt)
-        for k in WKEYS:
-            e = rel_err(w[k], rec["wtraj_" + k][it])
-            worst = max(worst, e)
-            assert e < REL, (it, k, e)
+        e = max(rel_err(w[k], rec["wtraj_" + k][it]) for k in WKEYS)
+        worst = max(worst, e)
+        if e >= REL and first_flip is None:
+            first_flip = it
+        assert e < (REL if first_flip is None else 2e-3), (it, e, first_flip)
         with torch.no_grad():
             tr = float(torch.nn.functional.mse_loss(model(tx), ty))
             va = float(torch.nn.functional.mse_loss(model(vx), vy))
-        assert abs(tr - rec["train_loss"][it]) < 1e-3 * rec["train_loss"][it], (it, tr, rec["train_loss"][it])
-        assert abs(va - rec["val_loss"][it]) < 1e-3 * rec["val_loss"][it], (it, va, rec["val_loss"][it])
-        if f"it{it}_gate_i" in rec:
+        tol = 1e-3 if first_flip is None else 3e-3
+        assert abs(tr - rec["train_loss"][it]) < tol * rec["train_loss"][it], (it, tr, rec["train_loss"][it])
+        assert abs(va - rec["val_loss"][it]) < tol * rec["val_loss"][it], (it, va, rec["val_loss"][it])
+        if f"it{it}_gate_i" in rec and first_flip is None:
             gates, duals = np_state(opt)
             rows = rec[f"it{it}_gate_i"].shape[0]
             for k in ("i", "f", "g", "o", "c", "h"):
@@ -163,7 +178,61 @@ def test_real_data_50_iterations(dataset, variant, params):
                 assert float(np.max(np.abs(duals[k][:rows] - rec[f"it{it}_dual_{k}"]))) < 1e-3 * scale, (it, k)
     assert abs(tr - rec["train_loss"][50]) < 0.01 * rec["train_loss"][50]
     assert abs(va - rec["val_loss"][50]) < 0.01 * rec["val_loss"][50]
-    print(f"{dataset}/{variant}: worst weight rel err over 50 iterations = {worst:.2e}")
+    if dataset != "googlestock":
+        assert first_flip is None, first_flip          # no knife edge on these data: strict 1e-4 throughout
+    print(f"{dataset}/{variant}: worst weight rel err over 50 iterations = {worst:.2e}, first theta flip at {first_flip}")
+
+
+@pytest.mark.parametrize("variant", ["admm", "no_dual_y"])
+def test_googlestock_50_iterations_decision_synchronised(variant):
+    """Arithmetic parity over 50 GoogleStock iterations with the backtracking decisions synchronised: the
+    oracle (pinned to the reference in test_oracle_golden.py) applies the theta the GPU chose; every
+    weight / gate / a must then agree to 1e-4 at every iteration.  Where the oracle's own loop would have
+    chosen differently, the comparison it lost must be a genuine knife edge (|f(beta)-est| tiny against
+    the terms compared), and such flips must be rare."""
+    _need_gpu()
+    from oracle.admm_oracle import OracleADMM
+    from gpu_utils import make_opt, np_state, weights_of
+    data = load("googlestock_data.npz")
+    rec = load(f"googlestock_{variant}.npz")
+    w0 = weights_from(rec, "init_")
+    _, opt = make_opt(w0, data["train_x"], data["train_y"], GOOGLE, variant)
+    ora = OracleADMM(w0, data["train_x"], data["train_y"], GOOGLE, variant=variant)
+    flips, noise_flips = [], []
+    for it in range(1, 51):
+        opt.step()
+        chosen = opt.theta_trace()
+        ora.forced = dict(chosen)
+        ora.step()
+        n_elem = data["train_x"].shape[0] * data["train_x"].shape[1] * opt.hidden_size
+        noise_floor = 100.0 * n_elem * (6e-8) ** 2
+        for name, th in chosen.items():
+            if name not in ora.trace or abs(ora.trace[name] - th) <= 1e-6 * th:
+                continue
+            assert name != "h_T", (it, ora.trace[name], th)      # the h_T loop has wide margins on these data
+            # the comparison at the smaller of the two thetas (x2: the un-halved value) decided it
+            th_dec = 2 * min(ora.trace[name], th)
+            cmp = [m for m in ora.margins[name] if abs(m[0] - th_dec) < 1e-9 * th_dec]
+            assert cmp, (it, name, ora.margins[name])
+            _, fb, est = cmp[0]
+            if max(fb, est) < noise_floor:
+                # f itself is rounding noise: a sum over N*T*H residuals that are each a cancellation at the
+                # fp32 ulp level (gate o early in the run; the "absorption exits" of SURVEY section 7).  Both
+                # implementations decide on noise there and the resulting step is ~1e-9 of the weight.
+                noise_flips.append((it, name, ora.trace[name], th))
+                continue
+            scale = max(abs(fb), abs(est), 1e-30)
+            assert abs(fb - est) < 1e-4 * scale, ("not a knife edge", it, name, fb, est)
+            flips.append((it, name, ora.trace[name], th, fb, est))
+        w = weights_of(opt)
+        gates, _ = np_state(opt)
+        for k in WKEYS:
+            assert rel_err(w[k], ora.w[k]) < REL, (it, k, rel_err(w[k], ora.w[k]))
+        for k in ("i", "f", "g", "o", "c", "h", "a"):
+            assert rel_err(gates[k], ora.gates[k]) < REL, (it, k)
+    print(f"googlestock/{variant}: {len(flips)} knife-edge theta flips vs the oracle's own decisions: {flips}; "
+          f"{len(noise_flips)} decisions taken on rounding noise by both sides")
+    assert len(flips) <= 8, flips
 
 
 @pytest.mark.parametrize("shape,params,variant,cls", [
@@ -315,3 +384,47 @@ def test_full_size_properties():
         assert float(a.gates[k][:, 0, :].abs().max()) == 0.0
     assert float(a.duals["h"][:, :t, :].abs().max()) == 0.0
     assert all(np.isfinite(v).all() for v in wa.values())
+
+
+@pytest.mark.parametrize("shape", [(256, 3, 16, 64, 1), (300, 2, 9, 128, 2), (1000, 2, 64, 256, 1)])
+def test_tensor_core_preactivations(shape):
+    """tcgen05 3xTF32 gate GEMM vs the fp32 CUDA-core GEMM and vs float64: the split product must be
+    fp32-accurate (plain TF32 would be ~1e-3 off)."""
+    _need_gpu()
+    from gpu_utils import make_opt
+    n, t, d, h, o = shape
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=h)
+    _, opt = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    assert opt.uses_tensor_cores
+    s = torch.cuda.current_stream().cuda_stream
+    hs = opt.gates["h"].cpu().numpy().astype(np.float64)
+    for tt in range(1, t + 1):
+        z_tc = torch.zeros((4, h, opt.ldn), device="cuda")
+        z_cc = torch.zeros((4, h, opt.ldn), device="cuda")
+        opt._call("admm_debug_preact", opt._pp, tt, z_tc.data_ptr(), 1, s)
+        opt._call("admm_debug_preact", opt._pp, tt, z_cc.data_ptr(), 0, s)
+        torch.cuda.synchronize()
+        ref = np.stack([x[:, tt - 1, :].astype(np.float64) @ w["x2" + g].astype(np.float64)
+                        + hs[:, tt - 1, :] @ w["h2" + g].astype(np.float64) for g in "ifgo"])      # [4][n][h]
+        ref = ref.transpose(0, 2, 1)
+        e_tc = np.max(np.abs(z_tc[:, :, :n].cpu().numpy() - ref)) / np.max(np.abs(ref))
+        e_cc = np.max(np.abs(z_cc[:, :, :n].cpu().numpy() - ref)) / np.max(np.abs(ref))
+        print(f"shape {shape} t={tt}: rel err vs f64  tcgen05 3xTF32 {e_tc:.2e}   fp32 FMA {e_cc:.2e}")
+        assert e_cc < 2e-6
+        assert e_tc < 4e-6      # ~2^-22 per product from the dropped lo*lo term and the tf32 rounding of the lo parts
+
+
+@pytest.mark.parametrize("variant,shape,params", [("admm", (384, 4, 16, 64, 1), GOOGLE), ("no_dual_y", (500, 3, 9, 128, 6), HAR)])
+def test_tensor_core_step_vs_oracle(variant, shape, params):
+    _need_gpu()
+    from oracle.admm_oracle import OracleADMM
+    from gpu_utils import make_opt
+    n, t, d, h, o = shape
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=11, classification=(o > 1))
+    _, opt = make_opt(w, x, y, params, variant, use_tensor_cores=True)
+    ora = OracleADMM(w, x, y, params, variant=variant)
+    _cmp_state(opt, ora, params, "init", rel=1e-5)
+    for s in range(3):
+        ora.step()
+        opt.step()
+        _cmp_state(opt, ora, params, f"tc step{s}")

@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libadmm_lstm_b200.so")
 
 ADMM_MAX_O = 16
-ADMM_MAX_CAND = 16
+ADMM_MAX_CAND = 32
 ADMM_N_METRICS = 8
 VARIANT_ADMM, VARIANT_NO_DUAL_Y = 0, 1
 SRC_X, SRC_H = 0, 1
@@ -55,7 +55,7 @@ SIGNATURES = {
     "admm_wy_apply": (C.c_int, [PP, vp, vp]),
     "admm_weight_grad": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "admm_weight_finish_grad": (C.c_int, [PP, C.c_int, vp, vp, vp]),
-    "admm_weight_probe": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]),
+    "admm_weight_probe": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
     "admm_weight_select": (C.c_int, [PP, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "admm_weight_apply": (C.c_int, [PP, C.c_int, vp, vp, vp]),
     "admm_sweep_t": (C.c_int, [PP, C.c_int, vp, vp]),

@@ -162,16 +162,20 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   ADMM_REQUIRE(scratch && g_acc && fw_acc, "admm_weight_grad: null buffers");
   cudaStream_t st = (cudaStream_t)stream;
   GateGemmArgs a = base_args(p, t0 + 1);
+  const bool use_tc = p->tc_ws && tc_eligible(p);
+  const bool atr_on_tc = use_tc && src == ADMM_SRC_H;
   a.scratch = scratch; a.tc = tc; a.fw_acc = fw_acc; a.src = src;
+  a.scratch_q = atr_on_tc ? scratch + 4LL * p->H * tc * p->ldn : nullptr;     // tf32 low part of R^T
   rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
   if (rc) return rc;
   AtrArgs r;
   r.ldn = p->ldn; r.H = p->H; r.tc = tc;
+  r.scratch_lo = a.scratch_q;
   r.K = (src == ADMM_SRC_X) ? p->D : p->H;
   r.a_src = (src == ADMM_SRC_X) ? a.x : a.h_prev;
   r.a_tstride = (int64_t)r.K * p->ldn;
   r.scratch = scratch; r.g_acc = g_acc;
-  if (p->tc_ws && tc_eligible(p) && src == ADMM_SRC_H) return atr_tc(p, r, st);
+  if (atr_on_tc) return atr_tc(p, r, st);
   return atr_simt(r, st);
 }
 
@@ -184,16 +188,28 @@ int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc,
   return ADMM_OK;
 }
 
-int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, const float* grad, int k0, int ncand,
-                      const int32_t* done, double* fk_acc, void* stream) {
+int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scratch, const float* grad, int k0,
+                      int ncand, const int32_t* done, double* fk_acc, void* stream) {
   int rc = validate(p, "admm_weight_probe");
   if (rc) return rc;
   ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_probe: bad src");
   ADMM_REQUIRE(t0 >= 0 && tc >= 1 && t0 + tc <= p->T, "admm_weight_probe: bad timestep range");
   ADMM_REQUIRE(ncand >= 1 && ncand <= ADMM_MAX_CAND && k0 >= 0 && k0 + ncand <= 120, "admm_weight_probe: bad candidates");
+  ADMM_REQUIRE(scratch && grad && done && fk_acc, "admm_weight_probe: null buffers");
+  cudaStream_t st = (cudaStream_t)stream;
   GateGemmArgs a = base_args(p, t0 + 1);
-  a.tc = tc; a.src = src; a.grad = grad; a.k0 = k0; a.ncand = ncand; a.done = done; a.fk_acc = fk_acc;
-  return run_gate_gemm(GG_PROBE, p, a, tc, (cudaStream_t)stream);
+  const int64_t half = 4LL * p->H * tc * p->ldn;
+  a.tc = tc; a.src = src; a.grad = grad; a.done = done;
+  a.scratch = scratch; a.scratch_q = scratch + half;
+  rc = run_gate_gemm(GG_PROBE, p, a, tc, st);
+  if (rc) return rc;
+  ProbeEvalArgs e;
+  e.n = p->n; e.ldn = p->ldn; e.H = p->H; e.tc = tc;
+  e.z0 = a.scratch; e.q = a.scratch_q;
+  for (int g = 0; g < 4; ++g) { e.gate[g] = a.gate[g]; e.dual[g] = a.dual[g]; e.rho[g] = p->hp.rho[g]; }
+  e.s_tstride = a.s_tstride;
+  e.k0 = k0; e.ncand = ncand; e.done = done; e.fk_acc = fk_acc;
+  return probe_eval(e, st);
 }
 
 int admm_weight_select(const admm_problem* p, int src, const float* grad, const double* fw_acc,
@@ -262,7 +278,6 @@ int admm_debug_preact(const admm_problem* p, int t, float* out, int use_tc, void
   ADMM_REQUIRE(t >= 1 && t <= p->T && out, "admm_debug_preact: bad arguments");
   GateGemmArgs a = base_args(p, t);
   a.scratch = out; a.tc = 1;
-  if (use_tc == 2) { a.dbg = out + 4LL * p->H * p->ldn; use_tc = 1; }
   if (use_tc) {
     ADMM_REQUIRE(p->tc_ws && tc_eligible(p), "admm_debug_preact: tensor-core path not available for this problem");
     return gate_gemm_tc(GG_RAWZ, p, a, 1, (cudaStream_t)stream);

@@ -26,16 +26,14 @@ struct GateGemmArgs {
   Rho rho;
   int32_t last;          // SWEEP: t == T
   double* metrics;       // SWEEP: [>=3] or nullptr
-  float* scratch;        // GRAD: R^T [4][H][tc][ldn]
+  float* scratch;        // GRAD: R^T [4][H][tc][ldn] ; PROBE: Z0 in the same layout
+  float* scratch_q;      // PROBE: Q = A_src G, same layout ; GRAD (tensor-core path): tf32 low part of R^T
   int32_t tc;
   double* fw_acc;        // GRAD: [4]
   int32_t src;           // PROBE: ADMM_SRC_*
   const float* grad;     // PROBE: G [4][K][H]
-  int32_t k0, ncand;     // PROBE: theta_k = 2^(k0+k), k < ncand
-  const int32_t* done;   // PROBE: [4]
-  double* fk_acc;        // PROBE: [4][NC] with NC = 8 if ncand <= 8 else ADMM_MAX_CAND
+  const int32_t* done;   // PROBE: [4], the launch is skipped on the device when all four are set
   void* tc_ws;           // tensor-core workspace or nullptr
-  float* dbg;            // debug dump buffer (RAWZ) or nullptr
   float* h_lo;           // slab t of the h - tf32(h) side buffer (tensor-core path) or nullptr
 };
 
@@ -48,9 +46,27 @@ struct AtrArgs {
   int32_t K, H, tc;
   const float* a_src;
   int64_t a_tstride;
-  const float* scratch;
+  const float* scratch;     // R^T
+  const float* scratch_lo;  // tf32 low part of R^T (tensor-core path) or nullptr
   double* g_acc;
 };
 int atr_simt(const AtrArgs& a, cudaStream_t st);
+
+// fk_acc[4][ADMM_MAX_CAND + 1] (fp64) += sum over the chunk of (act(Z0 + Q 2^-(k0+k)) - lambda/rho - gate)^2 for
+// k < ncand, and, in the last slot of each gate, the same sum at Q = 0, i.e. f(w)   (admm.py:316-325).
+struct ProbeEvalArgs {
+  int64_t n, ldn;
+  int32_t H, tc;
+  const float* z0;       // [4][H][tc][ldn]
+  const float* q;
+  const float* gate[4];  // gate_g slab of the first timestep of the chunk
+  const float* dual[4];
+  int64_t s_tstride;
+  float rho[4];
+  int32_t k0, ncand;
+  const int32_t* done;
+  double* fk_acc;
+};
+int probe_eval(const ProbeEvalArgs& a, cudaStream_t st);
 
 }  // namespace admm

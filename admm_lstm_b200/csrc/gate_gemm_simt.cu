@@ -6,7 +6,8 @@
 //   FORWARD : blocks/lstm.py:77-85      (state initialisation / prediction)
 //   SWEEP   : admm.py:345-351 + 504-510 (primal i,f,g,o,c,h then dual ascent at timestep t)
 //   GRAD    : admm.py:302-312           (R = (act z - lambda/rho - gate) act'(z) -> scratch, f(w) partial sums)
-//   PROBE   : admm.py:316-325           (f(w + G/theta_k) partial sums for a vector of theta_k in one pass)
+//   PROBE   : admm.py:316-325           (Z0 = A w + B w' and Q = A_src G -> scratch; probe_eval.cu then sums
+//                                        f(w + G/theta_k) for a vector of theta_k from them in one pass)
 //
 // This is the general path (any D, H) and the numerical reference for the tcgen05 path in
 // gate_gemm_tc.cu.  Data layout is feature-major ([.][H][ldn], sample index fastest), so every
@@ -22,19 +23,19 @@ constexpr int BK = 16;     // k-slab per pipeline stage
 constexpr int BJ = 32;     // hidden units per CTA (x 4 gates = 128 accumulator columns)
 constexpr int NTHREADS = 256;
 
-template <int MODE, int TM, int NC>
+template <int MODE, int TM>
 struct Smem {
   static constexpr int BM = 16 * TM;
   float a[2][BK][BM];
   float w[2][BK][4][BJ];
   float g[(MODE == GG_PROBE) ? 2 : 1][(MODE == GG_PROBE) ? BK : 1][4][(MODE == GG_PROBE) ? BJ : 1];
-  float red[((MODE == GG_PROBE) ? 4 * NC : 4) * (NTHREADS / 32)];
+  float red[4 * (NTHREADS / 32)];
 };
 
-template <int MODE, int TM, int NC>
+template <int MODE, int TM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gate_gemm_simt_kernel(const GateGemmArgs p) {
-  using S = Smem<MODE, TM, NC>;
+  using S = Smem<MODE, TM>;
   constexpr int BM = S::BM;
   constexpr int NV = TM / 4;            // float4 groups of samples per thread
   __shared__ __align__(16) S sm;
@@ -174,18 +175,7 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
   // ------------------------------------------------------------------ epilogues
   const Rho rho = p.rho;
   const int64_t soff = (int64_t)tl * p.s_tstride;     // slab offset of timestep t inside state tensors
-  float msum[(MODE == GG_PROBE) ? 4 * NC : 4];
-#pragma unroll
-  for (int k = 0; k < ((MODE == GG_PROBE) ? 4 * NC : 4); ++k) msum[k] = 0.f;
-
-  int done_g[4] = {0, 0, 0, 0};
-  float inv_theta[(MODE == GG_PROBE) ? NC : 1];
-  if (MODE == GG_PROBE) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) done_g[g] = p.done[g];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) inv_theta[k] = ldexpf(1.0f, -(p.k0 + k));
-  }
+  float msum[4] = {0.f, 0.f, 0.f, 0.f};
 
 #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
@@ -288,21 +278,9 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
       if (MODE == GG_PROBE) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (done_g[g]) continue;
-          const float4 lam4 = ld_stream(p.dual[g] + off);
-          const float4 gv4 = ld_stream(p.gate[g] + off);
-          const float lam[4] = {lam4.x, lam4.y, lam4.z, lam4.w};
-          const float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
-          const float rg = (g == 0) ? rho.i : (g == 1) ? rho.f : (g == 2) ? rho.g : rho.o;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (!ok[e]) continue;
-            const float lr = lam[e] / rg;
-            const float z0 = acc[g][jj][v * 4 + e], q = accq[g][jj][v * 4 + e];
-#pragma unroll
-            for (int k = 0; k < NC; ++k)
-              if (k < p.ncand) msum[g * NC + k] += probe_point(z0, q, inv_theta[k], lr, gv[e], g == 2);
-          }
+          const int64_t so = (((int64_t)g * H + j) * p.tc + tl) * ldn + n;
+          st_stream(p.scratch + so, make_float4(acc[g][jj][v * 4 + 0], acc[g][jj][v * 4 + 1], acc[g][jj][v * 4 + 2], acc[g][jj][v * 4 + 3]));
+          st_stream(p.scratch_q + so, make_float4(accq[g][jj][v * 4 + 0], accq[g][jj][v * 4 + 1], accq[g][jj][v * 4 + 2], accq[g][jj][v * 4 + 3]));
         }
       }
     }
@@ -318,16 +296,13 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
     float m4[4] = {msum[0], msum[1], msum[2], msum[3]};
     block_accumulate<4>(m4, sm.red, p.fw_acc);
   }
-  if (MODE == GG_PROBE) {
-    block_accumulate<4 * NC>(msum, sm.red, p.fk_acc);
-  }
 }
 
-template <int MODE, int TM, int NC>
+template <int MODE, int TM>
 int launch(const GateGemmArgs& a, int tc, cudaStream_t st) {
   constexpr int BM = 16 * TM;
   dim3 grid((unsigned)((a.n + BM - 1) / BM), (unsigned)((a.H + BJ - 1) / BJ), (unsigned)tc);
-  gate_gemm_simt_kernel<MODE, TM, NC><<<grid, NTHREADS, 0, st>>>(a);
+  gate_gemm_simt_kernel<MODE, TM><<<grid, NTHREADS, 0, st>>>(a);
   count_launch();
   return check_launch("gate_gemm_simt");
 }
@@ -338,13 +313,11 @@ int gate_gemm_simt(int mode, const GateGemmArgs& a, int tc, cudaStream_t st) {
   // Small shards get the 64-sample tile so that more CTAs are in flight.
   const bool small = a.n * ((a.H + BJ - 1) / BJ) * tc < (int64_t)128 * 148 * 2;
   switch (mode) {
-    case GG_FORWARD: return small ? launch<GG_FORWARD, 4, 1>(a, tc, st) : launch<GG_FORWARD, 8, 1>(a, tc, st);
-    case GG_SWEEP:   return small ? launch<GG_SWEEP, 4, 1>(a, tc, st) : launch<GG_SWEEP, 8, 1>(a, tc, st);
-    case GG_GRAD:    return small ? launch<GG_GRAD, 4, 1>(a, tc, st) : launch<GG_GRAD, 8, 1>(a, tc, st);
-    case GG_RAWZ:    return launch<GG_RAWZ, 4, 1>(a, tc, st);
-    case GG_PROBE:
-      if (a.ncand <= 8) return launch<GG_PROBE, 4, 8>(a, tc, st);
-      return launch<GG_PROBE, 4, ADMM_MAX_CAND>(a, tc, st);
+    case GG_FORWARD: return small ? launch<GG_FORWARD, 4>(a, tc, st) : launch<GG_FORWARD, 8>(a, tc, st);
+    case GG_SWEEP:   return small ? launch<GG_SWEEP, 4>(a, tc, st) : launch<GG_SWEEP, 8>(a, tc, st);
+    case GG_GRAD:    return small ? launch<GG_GRAD, 4>(a, tc, st) : launch<GG_GRAD, 8>(a, tc, st);
+    case GG_RAWZ:    return launch<GG_RAWZ, 4>(a, tc, st);
+    case GG_PROBE:   return launch<GG_PROBE, 4>(a, tc, st);
   }
   set_error("gate_gemm_simt: bad mode %d", mode);
   return ADMM_EINVAL;

@@ -121,29 +121,33 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
          ((uint32_t)(m >> 4) << 24);
 }
 
-template <int MODE>
 struct Cfg {
-  static constexpr bool PROBE = (MODE == GG_PROBE);
-  static constexpr int JC = PROBE ? 32 : 64;          // hidden units per tile
-  static constexpr int NCOL = 4 * JC;                 // accumulator columns of Z
-  static constexpr int TMEM_COLS = 256;               // Z (+ Q for PROBE)
+  static constexpr int JC = 64;                       // hidden units per tile
+  static constexpr int NCOL = 4 * JC;                 // accumulator columns: (gate, unit)
+  static constexpr int TMEM_COLS = 256;
   static constexpr int A_BYTES = BM * BK * 4;         // 8 KB
-  static constexpr int B_BYTES = NCOL * BK * 4;       // 16 KB (8 KB for PROBE)
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES + (PROBE ? 2 * B_BYTES : 0);
+  static constexpr int B_BYTES = NCOL * BK * 4;       // 16 KB
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
 };
 
+// k-block range [kb_begin, kb_end) over the concatenated feature axis (x blocks first, then h blocks) and the
+// choice of B operand: the gate weights (Z = x W + h U) or the probed weight's gradient (Q = A_src G).
+struct TcRange {
+  int kb_begin, kb_end;
+  int b_is_grad;      // 0: B = (wx | wh) hi/lo ; 1: B = gradient hi/lo, k relative to kb_begin
+};
 
-template <int MODE, int NC>
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 2)
-gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0) {
-  using C = Cfg<MODE>;
+gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0, const TcRange rng) {
+  using C = Cfg;
   constexpr int JC = C::JC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[4 * ADMM_MAX_CAND * 4];
+  __shared__ float red[4 * 4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BM;
@@ -152,7 +156,7 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
   const int D = p.D, H = p.H;
   const int nkx = (D + BK - 1) / BK, nkh = (H + BK - 1) / BK, nkb = nkx + nkh;
 
-  if (MODE == GG_PROBE) {
+  if (MODE == GG_RAWZ && p.done) {
     if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
   }
 
@@ -167,20 +171,19 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  const int q_lo = (MODE == GG_PROBE) ? (p.src == ADMM_SRC_X ? 0 : nkx) : 0;
-  const int q_hi = (MODE == GG_PROBE) ? (p.src == ADMM_SRC_X ? nkx : nkb) : 0;
+  (void)nkb;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % NSTAGE, it = kb / NSTAGE;
+      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
+        const int li = kb - rng.kb_begin;
+        const int s = li % NSTAGE, it = li / NSTAGE;
         if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
         const bool is_x = kb < nkx;
         const int k0 = (is_x ? kb : kb - nkx) * BK;
-        const bool qk = (MODE == GG_PROBE) && kb >= q_lo && kb < q_hi;
         uint8_t* st = smem + s * C::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES + (qk ? 2 * C::B_BYTES : 0));
+        mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES);
         const CUtensorMap* ma = is_x ? &maps.x : &maps.h;
         const CUtensorMap* ml = is_x ? &maps.x_lo : &maps.h_lo;
         const int slab = slab0 + tl;
@@ -189,60 +192,40 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
           tma_load_3d(st + c * CHUNK_BYTES, ma, &full_bar[s], n0 + 32 * c, k0, slab);
           tma_load_3d(st + C::A_BYTES + c * CHUNK_BYTES, ml, &full_bar[s], n0 + 32 * c, k0, slab);
         }
-        const CUtensorMap* bh = is_x ? &maps.wx_hi : &maps.wh_hi;
-        const CUtensorMap* bl = is_x ? &maps.wx_lo : &maps.wh_lo;
+        const CUtensorMap* bh = rng.b_is_grad ? &maps.gx_hi : (is_x ? &maps.wx_hi : &maps.wh_hi);
+        const CUtensorMap* bl = rng.b_is_grad ? &maps.gx_lo : (is_x ? &maps.wx_lo : &maps.wh_lo);
+        const int kb0 = rng.b_is_grad ? li * BK : k0;
         uint8_t* sb = st + 2 * C::A_BYTES;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
           for (int c = 0; c < JC / 32; ++c) {
             const int chunk = g * (JC / 32) + c;
-            tma_load_3d(sb + chunk * CHUNK_BYTES, bh, &full_bar[s], j0 + 32 * c, k0, g);
-            tma_load_3d(sb + C::B_BYTES + chunk * CHUNK_BYTES, bl, &full_bar[s], j0 + 32 * c, k0, g);
+            tma_load_3d(sb + chunk * CHUNK_BYTES, bh, &full_bar[s], j0 + 32 * c, kb0, g);
+            tma_load_3d(sb + C::B_BYTES + chunk * CHUNK_BYTES, bl, &full_bar[s], j0 + 32 * c, kb0, g);
           }
-        if (qk) {
-          uint8_t* sg = sb + 2 * C::B_BYTES;
-          const int kq = (kb - q_lo) * BK;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-#pragma unroll
-            for (int c = 0; c < JC / 32; ++c) {
-              const int chunk = g * (JC / 32) + c;
-              tma_load_3d(sg + chunk * CHUNK_BYTES, &maps.gx_hi, &full_bar[s], j0 + 32 * c, kq, g);
-              tma_load_3d(sg + C::B_BYTES + chunk * CHUNK_BYTES, &maps.gx_lo, &full_bar[s], j0 + 32 * c, kq, g);
-            }
-        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, C::NCOL);
-      bool first_q = true;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % NSTAGE, it = kb / NSTAGE;
+      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
+        const int li = kb - rng.kb_begin;
+        const int s = li % NSTAGE, it = li / NSTAGE;
         mbar_wait(&full_bar[s], it & 1);
         tc_fence_after();
-        const bool qk = (MODE == GG_PROBE) && kb >= q_lo && kb < q_hi;
         const uint32_t st = smem_u32(smem + s * C::STAGE_BYTES);
         const uint32_t a_hi = st, a_lo = st + C::A_BYTES;
         const uint32_t b_hi = st + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint32_t off = ks * 1024;
-          const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
+          const uint32_t acc0 = (li > 0 || ks > 0) ? 1u : 0u;
           umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc0);
           umma_tf32(tmem_base, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
           umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
-          if (qk) {
-            const uint32_t g_hi = b_hi + 2 * C::B_BYTES, g_lo = g_hi + C::B_BYTES;
-            const uint32_t accq = (first_q && ks == 0) ? 0u : 1u;
-            umma_tf32(tmem_base + C::NCOL, make_desc(a_hi + off), make_desc(g_hi + off), idesc, accq);
-            umma_tf32(tmem_base + C::NCOL, make_desc(a_lo + off), make_desc(g_hi + off), idesc, 1u);
-            umma_tf32(tmem_base + C::NCOL, make_desc(a_hi + off), make_desc(g_lo + off), idesc, 1u);
-          }
         }
-        if (qk) first_q = false;
         umma_commit(&empty_bar[s]);
       }
       umma_commit(&acc_bar);
@@ -257,40 +240,15 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const Rho rho = p.rho;
     const int64_t soff = (int64_t)tl * p.s_tstride;
-    constexpr int NM = (MODE == GG_PROBE) ? 4 * NC : 4;
-    float msum[NM];
-#pragma unroll
-    for (int k = 0; k < NM; ++k) msum[k] = 0.f;
-    int done_g[4] = {0, 0, 0, 0};
-    if (MODE == GG_PROBE) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) done_g[g] = p.done[g];
-    }
+    constexpr int NM = 4;
+    float msum[NM] = {0.f, 0.f, 0.f, 0.f};
 
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
-    if (MODE == GG_RAWZ && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-      const int et = threadIdx.x - 64;
-      const float* sf = reinterpret_cast<const float*>(smem);
-      for (int i = et; i < NSTAGE * C::STAGE_BYTES / 4; i += 128) p.dbg[i] = sf[i];
-      float* td = p.dbg + NSTAGE * C::STAGE_BYTES / 4;
-      for (int cb = 0; cb < 256; cb += 8) {
-        float v[8];
-        tmem_ld8(t_row + cb, v);
-        for (int e = 0; e < 8; ++e) td[row * 256 + cb + e] = v[e];
-      }
-      if (et == 0) { td[128 * 256] = __uint_as_float(tmem_base); }
-    }
-
     for (int jb = 0; jb < JC; jb += 8) {
       float z[4][8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld8(t_row + g * JC + jb, z[g]);
-      float q[(MODE == GG_PROBE) ? 4 : 1][8];
-      if (MODE == GG_PROBE) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld8(t_row + C::NCOL + g * JC + jb, q[g]);
-      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int j = j0 + jb + e;
@@ -335,30 +293,19 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
             const float rg = (g == 0) ? rho.i : (g == 1) ? rho.f : (g == 2) ? rho.g : rho.o;
             float u;
             const float rr = grad_point(z[g][e], p.dual[g][off], p.gate[g][off], rg, g == 2, &u);
-            p.scratch[(((int64_t)g * H + j) * p.tc + tl) * ldn + n] = ok ? rr : 0.f;
+            const float rv = ok ? rr : 0.f;
+            const int64_t so = (((int64_t)g * H + j) * p.tc + tl) * ldn + n;
+            p.scratch[so] = rv;
+            if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv);
             if (ok) msum[g] += u * u;
-          }
-        }
-        if (MODE == GG_PROBE) {
-          if (ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (done_g[g]) continue;
-              const float rg = (g == 0) ? rho.i : (g == 1) ? rho.f : (g == 2) ? rho.g : rho.o;
-              const float lr = p.dual[g][off] / rg, gv = p.gate[g][off];
-#pragma unroll
-              for (int k = 0; k < NC; ++k)
-                if (k < p.ncand)
-                  msum[g * NC + k] += probe_point(z[g][e], q[g][e], ldexpf(1.0f, -(p.k0 + k)), lr, gv, g == 2);
-            }
           }
         }
       }
     }
     tc_fence_before();
     // block-level reduction of the metric partials over the 4 epilogue warps
-    if (MODE == GG_SWEEP || MODE == GG_GRAD || MODE == GG_PROBE) {
-      double* dst = (MODE == GG_SWEEP) ? p.metrics : (MODE == GG_GRAD) ? p.fw_acc : p.fk_acc;
+    if (MODE == GG_SWEEP || MODE == GG_GRAD) {
+      double* dst = (MODE == GG_SWEEP) ? p.metrics : p.fw_acc;
       constexpr int NOUT = (MODE == GG_SWEEP) ? 3 : NM;
       if (dst) {
 #pragma unroll
@@ -501,16 +448,17 @@ int get_maps(const admm_problem* p, int src, TcMaps* out) {
   return rc ? ADMM_ECUDA : ADMM_OK;
 }
 
-template <int MODE, int NC>
-int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, int slab0, int tc, cudaStream_t st) {
-  using C = Cfg<MODE>;
+template <int MODE>
+int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, int slab0, int tc, const TcRange& rng,
+              cudaStream_t st) {
+  using C = Cfg;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gate_gemm_tc_kernel<MODE, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(gate_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     configured = true;
   }
   dim3 grid((unsigned)(p->ldn / BM), (unsigned)(p->H / C::JC), (unsigned)tc);
-  gate_gemm_tc_kernel<MODE, NC><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a, maps, slab0);
+  gate_gemm_tc_kernel<MODE><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a, maps, slab0, rng);
   count_launch();
   return check_launch("gate_gemm_tc");
 }
@@ -576,19 +524,199 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   const int64_t slab_elems = (int64_t)p->H * p->ldn;
   const int slab0 = (int)((a.h_prev - p->gate[5]) / slab_elems);
   a.h_lo = tc_h_lo(p) + (a.gate[5] - p->gate[5]);
+  const int nkx = (p->D + BK - 1) / BK, nkh = (p->H + BK - 1) / BK;
+  const TcRange full{0, nkx + nkh, 0};
   switch (mode) {
-    case GG_FORWARD: return launch_tc<GG_FORWARD, 1>(p, a, maps, slab0, tc, st);
-    case GG_SWEEP: return launch_tc<GG_SWEEP, 1>(p, a, maps, slab0, tc, st);
-    case GG_GRAD: return launch_tc<GG_GRAD, 1>(p, a, maps, slab0, tc, st);
-    case GG_PROBE:
-      if (a.ncand <= 8) return launch_tc<GG_PROBE, 8>(p, a, maps, slab0, tc, st);
-      return launch_tc<GG_PROBE, ADMM_MAX_CAND>(p, a, maps, slab0, tc, st);
-    case GG_RAWZ: return launch_tc<GG_RAWZ, 1>(p, a, maps, slab0, tc, st);
+    case GG_FORWARD: return launch_tc<GG_FORWARD>(p, a, maps, slab0, tc, full, st);
+    case GG_SWEEP: return launch_tc<GG_SWEEP>(p, a, maps, slab0, tc, full, st);
+    case GG_GRAD: return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, full, st);
+    case GG_RAWZ: return launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st);
+    case GG_PROBE: {
+      // Z0 = x W + h U, then Q = A_src G: two launches of the same kernel (each keeps the 64-unit tile and
+      // two resident CTAs per SM; a fused Z0|Q tile needs all 512 TMEM columns and halves the tile width)
+      rc = launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st);
+      if (rc) return rc;
+      GateGemmArgs q = a;
+      q.scratch = a.scratch_q;
+      const TcRange qr = (a.src == ADMM_SRC_X) ? TcRange{0, nkx, 1} : TcRange{nkx, nkx + nkh, 1};
+      return launch_tc<GG_RAWZ>(p, q, maps, slab0, tc, qr, st);
+    }
   }
   set_error("gate_gemm_tc: bad mode %d", mode);
   return ADMM_EINVAL;
 }
 
-int atr_tc(const admm_problem*, const AtrArgs& a, cudaStream_t st) { return atr_simt(a, st); }
+namespace {
+// ------------------------------------------------------------------------------------------------------------
+// G^T tile on the tensor cores (admm.py:308-311):   G_acc[g][k][j] += sum_{t,n} R[(g,j)][t][n] * h_{t-1}[k][n]
+// Both operands are contiguous along the reduction index n, i.e. K-major for UMMA: plain SWIZZLE_128B boxes of
+// 32 samples.  D rows (TMEM lanes) = 128 consecutive (gate, unit) columns of G, D columns = NT rows k of G, so the
+// epilogue's accumulation into the fp64 G buffer is coalesced along j.  3xTF32: R_hi*h_hi + R_lo*h_hi + R_hi*h_lo.
+constexpr int ATR_BKN = 32;           // samples per pipeline stage (one 128-byte swizzle row)
+constexpr int ATR_STAGES = 2;
+
+struct AtrMaps { CUtensorMap r, r_lo, h, h_lo; };
+
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_kmajor(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int NT_>
+__global__ void __launch_bounds__(NTHREADS, 1)
+atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H, int tc, int64_t ldn, int slab0,
+              int chunks_per_cta, int n_chunks, int use_atomics) {
+  constexpr int A_BYTES = 128 * ATR_BKN * 4;        // R tile   16 KB
+  constexpr int B_BYTES = NT_ * ATR_BKN * 4;        // h tile   NT x 128 B
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[ATR_STAGES], empty_bar[ATR_STAGES], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 128;          // first (gate, unit) column of G handled here
+  const int k0 = blockIdx.y * NT_;          // first row k of G
+  const int ch_begin = blockIdx.z * chunks_per_cta;
+  const int ch_end = min(ch_begin + chunks_per_cta, n_chunks);
+  if (ch_begin >= ch_end) return;
+  const int chunks_per_t = (int)(ldn / ATR_BKN);
+  constexpr int TCOLS = NT_ < 32 ? 32 : NT_;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ATR_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int li = ch - ch_begin, s = li % ATR_STAGES, it = li / ATR_STAGES;
+        if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
+        const int tl = ch / chunks_per_t, n0 = (ch % chunks_per_t) * ATR_BKN;
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_3d(st, &maps.r, &full_bar[s], n0, tl, c0);
+        tma_load_3d(st + A_BYTES, &maps.r_lo, &full_bar[s], n0, tl, c0);
+        tma_load_3d(st + 2 * A_BYTES, &maps.h, &full_bar[s], n0, k0, slab0 + tl);
+        tma_load_3d(st + 2 * A_BYTES + B_BYTES, &maps.h_lo, &full_bar[s], n0, k0, slab0 + tl);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_kmajor(128, NT_);
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int li = ch - ch_begin, s = li % ATR_STAGES, it = li / ATR_STAGES;
+        mbar_wait(&full_bar[s], it & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t r_hi = st, r_lo = st + A_BYTES, h_hi = st + 2 * A_BYTES, h_lo = h_hi + B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < ATR_BKN / 8; ++ks) {
+          const uint32_t off = ks * 32;                 // 8 floats inside the 128-byte swizzle row
+          umma_tf32(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_hi + off), idesc, (li > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, make_desc_k128(r_lo + off), make_desc_k128(h_hi + off), idesc, 1u);
+          umma_tf32(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_lo + off), idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int c = c0 + quarter * 32 + lane;            // (gate, unit) column of G owned by this thread
+    const int g = c / H, j = c % H;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    for (int kb = 0; kb < NT_; kb += 8) {
+      float v[8];
+      tmem_ld8(t_row + kb, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + kb + e;
+        if (k < K) {
+          double* dst = g_acc + ((int64_t)g * K + k) * H + j;
+          if (use_atomics) atomicAdd(dst, (double)v[e]);
+          else *dst += (double)v[e];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TCOLS);
+  }
+}
+
+int make_map_box(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                 uint64_t stride2_elems, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADMM_ECUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 4, stride2_elems * 4};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (atr) failed (%d)", (int)r); return ADMM_ECUDA; }
+  return ADMM_OK;
+}
+
+template <int NT_>
+int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, cudaStream_t st) {
+  constexpr int SMEM = ATR_STAGES * (2 * 128 * ATR_BKN * 4 + 2 * NT_ * ATR_BKN * 4) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(atr_tc_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    configured = true;
+  }
+  AtrMaps m;
+  const uint64_t ldn = a.ldn, H = a.H, tc = a.tc, T1 = p->T + 1;
+  int rc = 0;
+  rc |= make_map_box(&m.r, a.scratch, ldn, tc, 4 * H, ldn, tc * ldn, ATR_BKN, 1, 128);
+  rc |= make_map_box(&m.r_lo, a.scratch_lo, ldn, tc, 4 * H, ldn, tc * ldn, ATR_BKN, 1, 128);
+  rc |= make_map_box(&m.h, p->gate[5], ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
+  rc |= make_map_box(&m.h_lo, tc_h_lo(p), ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
+  if (rc) return ADMM_ECUDA;
+  const int n_chunks = (int)(tc * (ldn / ATR_BKN));
+  const int tiles = (int)((4 * H / 128) * ((H + NT_ - 1) / NT_));
+  int splits = (148 + tiles - 1) / tiles;
+  if (tiles * splits > 148 && splits > 1) --splits;          // stay within one wave of 148 single-CTA SMs
+  splits = max(1, min(splits, n_chunks));
+  const int cpc = (n_chunks + splits - 1) / splits;
+  splits = (n_chunks + cpc - 1) / cpc;
+  dim3 grid((unsigned)(4 * H / 128), (unsigned)((H + NT_ - 1) / NT_), (unsigned)splits);
+  atr_tc_kernel<NT_><<<grid, NTHREADS, SMEM, st>>>(m, a.g_acc, a.K, a.H, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1);
+  count_launch();
+  return check_launch("atr_tc");
+}
+
+}  // namespace
+
+// Tensor-core G += A_src^T R for src = h (K = H).  `a.a_src` must be a slab of p->gate[5].
+int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st) {
+  if (!a.scratch_lo || a.K != p->H) return atr_simt(a, st);
+  const int slab0 = (int)((a.a_src - p->gate[5]) / ((int64_t)p->H * p->ldn));
+  if (p->H >= 256) return launch_atr<256>(p, a, slab0, st);
+  if (p->H >= 128) return launch_atr<128>(p, a, slab0, st);
+  return launch_atr<64>(p, a, slab0, st);
+}
 
 }  // namespace admm

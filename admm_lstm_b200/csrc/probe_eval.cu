@@ -1,0 +1,148 @@
+// probe_eval.cu -- the backtracking probes of the weight update (admm.py:316-325, 331-336) for a whole vector
+// of candidate thetas in ONE pass over the data:
+//
+//   f_k = sum_{t,n,j} ( act(Z0 + Q * 2^-(k0+k)) - lambda/rho - gate )^2 ,   k = 0..ncand-1,   and f(w) at Q = 0
+//
+// Z0 = A w + B w' and Q = A_src G come from the gate GEMM (PROBE mode).  beta_k = w + G/theta_k, so
+// A beta_k + B w' = Z0 + Q/theta_k: the reference re-runs the full GEMM for every probe (and f(w) again inside
+// every est()), this kernel re-uses one GEMM for all of them.  Pure elementwise work at full occupancy:
+// float4 loads, per-thread fp32 partials, one fp64 atomic per (block, candidate).
+//
+// Activations: the kernel evaluates (ncand+1) * 4H activations per sample-timestep, so they are hand-rolled to
+// two MUFU ops each (ex2.approx + rcp.approx with one Newton step) plus a degree-5 odd polynomial for
+// |x| < 0.6 in tanh, where the exponential form loses relative accuracy.  Max error ~2 ulp, the same class as
+// expf()/tanhf() (a plain ex2/rcp tanh without the polynomial was measured to flip backtracking decisions whenever
+// a constraint residual sits at the fp32 rounding level, moving the trajectory by ~1e-3).  The sums only feed
+// the comparison f(beta) > est; f(w) comes from the same functions; state is never written from them.
+#include "common.cuh"
+#include "gate_gemm.h"
+
+namespace admm {
+namespace {
+
+constexpr int NT = 256;
+constexpr int JB = 8;          // hidden units per block
+constexpr int NCS = ADMM_MAX_CAND + 1;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1/d for d in [1, inf): rcp.approx + one Newton step (~0.5 ulp)
+__device__ __forceinline__ float rcp_polished(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+__device__ __forceinline__ float sigmoid_2mufu(float x) {
+  const float e = ex2_approx(-1.4426950408889634f * fmaxf(x, -80.0f));
+  return rcp_polished(1.0f + e);
+}
+__device__ __forceinline__ float tanh_2mufu(float x) {
+  const float ax = fminf(fabsf(x), 40.0f);
+  const float e = ex2_approx(-2.8853900817779268f * ax);
+  const float big = (1.0f - e) * rcp_polished(1.0f + e);
+  const float t = x * x;
+  float p = 0.0024976127315312624f;
+  p = fmaf(p, t, -0.008506525307893753f);
+  p = fmaf(p, t, 0.02181374467909336f);
+  p = fmaf(p, t, -0.05396425351500511f);
+  p = fmaf(p, t, 0.133333221077919f);
+  p = fmaf(p, t, -0.3333333432674408f);
+  const float small = fmaf(x * t, p, x);
+  return ax < 0.6f ? small : copysignf(big, x);
+}
+
+template <int NC, bool IS_G>
+__device__ __forceinline__ void accumulate(const float4& z4, const float4& q4, const float4& lam4, const float4& gv4,
+                                           float rho, const float (&inv_theta)[NC], const bool (&ok)[4],
+                                           float (&acc)[NC + 1]) {
+  const float z[4] = {z4.x, z4.y, z4.z, z4.w}, q[4] = {q4.x, q4.y, q4.z, q4.w};
+  const float lam[4] = {lam4.x, lam4.y, lam4.z, lam4.w}, gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (!ok[e]) continue;
+    const float lr = lam[e] / rho;
+#pragma unroll
+    for (int k = 0; k <= NC; ++k) {
+      const float zz = (k < NC) ? fmaf(q[e], inv_theta[k], z[e]) : z[e];
+      const float a = IS_G ? tanh_2mufu(zz) : sigmoid_2mufu(zz);
+      const float u = (a - lr) - gv[e];
+      acc[k] = fmaf(u, u, acc[k]);
+    }
+  }
+}
+
+// Work item = (gate g, timestep tl, block of JB units, block of 4*NT samples).  The grid is a fixed number of
+// CTAs that stride over the items: a launch whose gates are all decided (the speculative later passes of the
+// backtracking) then costs a few hundred CTAs that exit at once instead of one CTA per item.
+template <int NC>
+__global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, int n_jb, int n_nb, int64_t n_items) {
+  __shared__ float red[(NC + 1) * (NT / 32)];
+  if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
+  float inv_theta[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) inv_theta[k] = (k < p.ncand) ? ldexpf(1.0f, -(p.k0 + k)) : 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int nb = (int)(item % n_nb);
+    const int jb = (int)((item / n_nb) % n_jb);
+    const int gt = (int)(item / ((int64_t)n_nb * n_jb));
+    const int g = gt & 3, tl = gt >> 2;
+    if (p.done[g]) continue;
+    const int64_t n = ((int64_t)nb * NT + threadIdx.x) * 4;
+    const int j0 = jb * JB;
+    float acc[NC + 1];
+#pragma unroll
+    for (int k = 0; k <= NC; ++k) acc[k] = 0.f;
+    const float rho = p.rho[g];
+    if (n < p.ldn) {
+      const bool ok[4] = {n + 0 < p.n, n + 1 < p.n, n + 2 < p.n, n + 3 < p.n};
+      const float* gate = p.gate[g] + (int64_t)tl * p.s_tstride + n;
+      const float* dual = p.dual[g] + (int64_t)tl * p.s_tstride + n;
+#pragma unroll 2
+      for (int jj = 0; jj < JB; ++jj) {
+        const int j = j0 + jj;
+        if (j >= p.H) break;
+        const int64_t so = (((int64_t)g * p.H + j) * p.tc + tl) * p.ldn + n;
+        const float4 z4 = ld_stream(p.z0 + so), q4 = ld_stream(p.q + so);
+        const float4 lam4 = ld_stream(dual + (int64_t)j * p.ldn), gv4 = ld_stream(gate + (int64_t)j * p.ldn);
+        if (g == 2) accumulate<NC, true>(z4, q4, lam4, gv4, rho, inv_theta, ok, acc);
+        else accumulate<NC, false>(z4, q4, lam4, gv4, rho, inv_theta, ok, acc);
+      }
+    }
+    // candidates beyond ncand were evaluated at Q*0 (= f(w)); only slots < ncand and the f(w) slot are published
+#pragma unroll
+    for (int k = 0; k <= NC; ++k) {
+      const float s = warp_sum(acc[k]);
+      if (lane == 0) red[k * (NT / 32) + warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x <= NC) {
+      const int k = threadIdx.x;
+      if (k < p.ncand || k == NC) {
+        double s = 0.0;
+        for (int w = 0; w < NT / 32; ++w) s += (double)red[k * (NT / 32) + w];
+        atomicAdd(p.fk_acc + g * NCS + (k == NC ? ADMM_MAX_CAND : k), s);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int probe_eval(const ProbeEvalArgs& a, cudaStream_t st) {
+  const int n_nb = (int)((a.ldn / 4 + NT - 1) / NT), n_jb = (a.H + JB - 1) / JB;
+  const int64_t n_items = (int64_t)n_nb * n_jb * 4 * a.tc;
+  const unsigned grid = (unsigned)(n_items < 148 * 8 ? n_items : 148 * 8);
+  if (a.ncand <= 8) probe_eval_kernel<8><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
+  else if (a.ncand <= 16) probe_eval_kernel<16><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
+  else probe_eval_kernel<ADMM_MAX_CAND><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
+  count_launch();
+  return check_launch("probe_eval");
+}
+
+}  // namespace admm

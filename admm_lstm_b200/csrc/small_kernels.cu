@@ -324,11 +324,12 @@ __global__ void __launch_bounds__(256) weight_select_kernel(const float* w_all, 
   __syncthreads();
   if (threadIdx.x == 0) {
     const float rho = hp.rho[g];
-    const float f_w = 0.5f * rho * (float)fw_acc[g];
+    (void)fw_acc;
+    const float f_w = 0.5f * rho * (float)fk_acc[g * (ADMM_MAX_CAND + 1) + ADMM_MAX_CAND];
     int found = -1;
     for (int k = 0; k < ncand; ++k) {
       const float theta = ldexpf(1.0f, k0 + k);
-      const float f_b = 0.5f * rho * (float)fk_acc[g * NC + k];
+      const float f_b = 0.5f * rho * (float)fk_acc[g * (ADMM_MAX_CAND + 1) + k];
       const float est = f_w + (float)tot[k] + ((float)T * 0.5f * theta) * (float)tot[NC + k];
       if (!(f_b > est)) { found = k; break; }
     }
@@ -404,6 +405,9 @@ int launch_weight_select(const admm_problem& p, int src, const float* grad, cons
   if (ncand <= 8)
     weight_select_kernel<8><<<4, 256, 0, st>>>(w, grad, fw_acc, fk_acc, p.hp, p.T, per_gate, k0, ncand, final_pass,
                                                done, theta);
+  else if (ncand <= 16)
+    weight_select_kernel<16><<<4, 256, 0, st>>>(w, grad, fw_acc, fk_acc, p.hp, p.T, per_gate, k0, ncand, final_pass,
+                                                done, theta);
   else
     weight_select_kernel<ADMM_MAX_CAND><<<4, 256, 0, st>>>(w, grad, fw_acc, fk_acc, p.hp, p.T, per_gate, k0, ncand,
                                                            final_pass, done, theta);

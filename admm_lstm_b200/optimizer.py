@@ -160,20 +160,24 @@ class ADMMBasedOptimizer(object):
         kmax = max(D, H)
         self._acc_wy = torch.zeros(H * O, dtype=torch.float64, device=dev)
         self._acc_grad = torch.zeros(4 * kmax * H + 4, dtype=torch.float64, device=dev)   # [G_acc | f(w)]
-        self._acc_fk = torch.zeros(4 * _lib.ADMM_MAX_CAND, dtype=torch.float64, device=dev)
+        self._acc_fk = torch.zeros(4 * (_lib.ADMM_MAX_CAND + 1), dtype=torch.float64, device=dev)
         self._acc_last = torch.zeros(1 + 3 * 4, dtype=torch.float64, device=dev)
         self._metrics = torch.zeros(_lib.ADMM_N_METRICS, dtype=torch.float64, device=dev)
         self._grad = torch.zeros(4 * kmax * H, dtype=f32, device=dev)
         self._done = torch.zeros(4, dtype=torch.int32, device=dev)
         self._theta_w = torch.zeros(8, dtype=f32, device=dev)       # [src][gate]
         self._theta_h = torch.zeros(1, dtype=f32, device=dev)
-        self._theta_host = torch.zeros(9, dtype=f32).pin_memory()
-        self._theta_event: Optional[torch.cuda.Event] = None
+        # ring of pinned read-backs of the chosen thetas: the host runs ahead of the device (it is throttled only
+        # by the launch queue), so the hint for step s usually comes from step s-2
+        self._theta_ring = [[torch.zeros(9, dtype=f32).pin_memory(), None, -1] for _ in range(4)]
+        self._step_index = 0
         self._first_cand = {_lib.SRC_X: _lib.ADMM_MAX_CAND, _lib.SRC_H: _lib.ADMM_MAX_CAND}
 
-        budget = scratch_bytes if scratch_bytes is not None else int(os.environ.get("ADMM_LSTM_SCRATCH_BYTES", 1 << 30))
-        self._tc_chunk = max(1, min(T, budget // (16 * H * self.ldn)))
-        self._scratch = torch.empty(4 * H * self._tc_chunk * self.ldn, dtype=f32, device=dev)
+        # scratch of the weight phase: R^T for the gradient pass, Z0 and Q for the probe pass -> 8*H*ldn floats
+        # per timestep of a chunk
+        budget = scratch_bytes if scratch_bytes is not None else int(os.environ.get("ADMM_LSTM_SCRATCH_BYTES", 4 << 30))
+        self._tc_chunk = max(1, min(T, budget // (32 * H * self.ldn)))
+        self._scratch = torch.empty(8 * H * self._tc_chunk * self.ldn, dtype=f32, device=dev)
 
         # ---- C problem descriptor --------------------------------------------------------------------
         p = _lib.Problem()
@@ -366,14 +370,35 @@ class ADMMBasedOptimizer(object):
         return [(t0, min(tc, T - t0)) for t0 in range(0, T, tc)]
 
     def _poll_theta_hint(self) -> None:
-        """Non-blocking: use the previous step's theta (if its copy has landed) to size the first probe pass."""
-        if self._theta_event is not None and self._theta_event.query():
-            th = self._theta_host[:8].view(2, 4)
-            for src in (_lib.SRC_X, _lib.SRC_H):
-                kmax = float(th[src].max())
-                # theta_out = 2^(k-1) for exit index k; a first pass of 8 candidates covers k <= 7, keep 2 spare
-                self._first_cand[src] = 8 if 0 < kmax <= 16.0 else _lib.ADMM_MAX_CAND
-            self._theta_event = None
+        """Size the first probe pass of step s from the thetas chosen in step s-2.
+
+        The schedule must be identical on every rank (the per-pass candidate sums are all-reduced), so it may
+        only depend on replicated data, never on timing: the thetas are replicated, and "step s-2" is a fixed
+        choice.  Waiting for that read-back costs nothing in steady state: the host is throttled by the launch
+        queue to less than one step ahead of the device."""
+        want = self._step_index - 2
+        slot = self._theta_ring[want % len(self._theta_ring)] if want >= 0 else None
+        if slot is None or slot[2] != want:
+            self._first_cand = {_lib.SRC_X: _lib.ADMM_MAX_CAND, _lib.SRC_H: _lib.ADMM_MAX_CAND}
+            return
+        slot[1].synchronize()
+        th = slot[0][:8].view(2, 4)
+        for src in (_lib.SRC_X, _lib.SRC_H):
+            kmax = float(th[src].max())
+            # theta_out = 2^(k-1) for exit index k: a first pass of C candidates covers k <= C-1; keep 2 spare, so
+            # that the next step almost always needs a single GEMM pass
+            need = (int(kmax).bit_length() + 3) if kmax >= 1.0 else 3
+            self._first_cand[src] = 8 if need <= 8 else 16 if need <= 16 else _lib.ADMM_MAX_CAND
+
+    def _push_theta_hint(self) -> None:
+        slot = self._theta_ring[self._step_index % len(self._theta_ring)]
+        if slot[1] is not None:
+            slot[1].synchronize()       # four steps old: long finished
+        slot[0][:8].copy_(self._theta_w, non_blocking=True)
+        slot[0][8:].copy_(self._theta_h, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        slot[2] = self._step_index
 
     # ------------------------------------------------------------------------------------ step
     def step(self) -> None:
@@ -394,11 +419,8 @@ class ADMMBasedOptimizer(object):
         self._mark("sweep")
         self.__update_last(st)
         self._mark("last")
-        if self._theta_event is None:
-            self._theta_host[:8].copy_(self._theta_w, non_blocking=True)
-            self._theta_host[8:].copy_(self._theta_h, non_blocking=True)
-            self._theta_event = torch.cuda.Event()
-            self._theta_event.record()
+        self._push_theta_hint()
+        self._step_index += 1
 
     def __update_wy(self, st) -> None:
         """admm.py:246-280 / admm.no_dual_y.py:226-249."""
@@ -426,11 +448,11 @@ class ADMMBasedOptimizer(object):
         self._done.zero_()
         theta_ptr = self._theta_w[4 * src:].data_ptr()
         first = self._first_cand[src]
-        passes = [(0, first)] + [(first + 16 * q, _lib.ADMM_MAX_CAND) for q in range(3)]
+        passes = [(0, first)] + [(first + _lib.ADMM_MAX_CAND * q, _lib.ADMM_MAX_CAND) for q in range(2)]
         for q, (k0, ncand) in enumerate(passes):
             self._acc_fk.zero_()
             for t0, tc in chunks:
-                self._call("admm_weight_probe", pp, src, t0, tc, self._grad.data_ptr(), k0, ncand,
+                self._call("admm_weight_probe", pp, src, t0, tc, self._scratch.data_ptr(), self._grad.data_ptr(), k0, ncand,
                            self._done.data_ptr(), self._acc_fk.data_ptr(), st)
             self.comm.allreduce_sum_(self._acc_fk)
             self._call("admm_weight_select", pp, src, self._grad.data_ptr(), fw_ptr, self._acc_fk.data_ptr(),

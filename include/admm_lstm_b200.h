@@ -42,7 +42,7 @@ extern "C" {
 #define ADMM_SRC_H 1  /* map_from == 'h' : U  = h2g [H,H] */
 
 #define ADMM_MAX_O 16         /* output_size limit of the t = T kernels */
-#define ADMM_MAX_CAND 16      /* theta candidates per probe pass        */
+#define ADMM_MAX_CAND 32      /* theta candidates per probe pass        */
 #define ADMM_N_METRICS 8
 
 /* rho / beta in the reference's own key order (admm.py:131-160, parameters.py). */
@@ -112,21 +112,23 @@ int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream);
  * couple in the weight phase).
  *  grad   : for timesteps t0 < t <= t0+tc: z = x_t W + h_{t-1} U; R = (act z - lambda/rho - gate) act'(z);
  *           g_acc[4][K][H] (fp64) += A_src^T R;  fw_acc[4] (fp64) += sum (act z - lambda/rho - gate)^2.
- *           scratch: 4*H*tc*ldn floats.
+ *           scratch: 8*H*tc*ldn floats (R^T and, on the tensor-core path, its tf32 low part).
  *  finish : G = rho_g * (float) g_acc  -> grad_out [4][K][H] fp32           (admm.py:312)
- *  probe  : fk_acc[4][ncand] (fp64) += sum (act(z + (A_src G)/theta_k) - lambda/rho - gate)^2 for
- *           theta_k = 2^(k0+k); gates with done[g] != 0 are skipped       (admm.py:316-325, 331-336)
+ *  probe  : fk_acc[4][ADMM_MAX_CAND+1] (fp64) += sum (act(z + (A_src G)/theta_k) - lambda/rho - gate)^2 for
+ *           theta_k = 2^(k0+k), k < ncand, and in slot ADMM_MAX_CAND the same sum at G = 0, i.e. f(w);
+ *           gates with done[g] != 0 are skipped (admm.py:316-325, 331-336).  scratch: 8*H*tc*ldn floats.
  *  select : per gate, replays `while f(beta) > est(beta, theta): theta *= 2` (admm.py:331-338) over the
- *           candidates k0..k0+ncand-1 from the reduced sums; writes theta_out[g] (already halved,
- *           admm.py:338) and done[g].
+ *           candidates k0..k0+ncand-1 from the reduced sums (f(w) is taken from fk_acc's last slot, so both
+ *           sides of the comparison come from the same kernel); writes theta_out[g] (already halved,
+ *           admm.py:338) and done[g].  fw_acc (from grad) is kept for reporting only.
  *  apply  : w <- (0.5 rho T theta w - G)/(beta + 0.5 rho theta T)           (admm.py:340-343)
  * K = D for ADMM_SRC_X, H for ADMM_SRC_H. */
 int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scratch,
                      double* g_acc, double* fw_acc, void* stream);
 int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out,
                             void* stream);
-int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, const float* grad, int k0,
-                      int ncand, const int32_t* done, double* fk_acc, void* stream);
+int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scratch, const float* grad,
+                      int k0, int ncand, const int32_t* done, double* fk_acc, void* stream);
 int admm_weight_select(const admm_problem* p, int src, const float* grad, const double* fw_acc,
                        const double* fk_acc, int k0, int ncand, int final_pass, int32_t* done,
                        float* theta_out, void* stream);

@@ -257,8 +257,11 @@ def test_random_shapes_vs_oracle(shape, params, variant, cls):
         opt.step()
         _cmp_state(opt, ora, params, f"step{s}")
         m_o, m_g = ora.metrics(prev), opt.metrics()
+        # the residual norms are differences of O(1) state entries: a 1e-4-relative state agreement bounds them
+        # absolutely, by ~1e-6 * sqrt(number of entries)
+        atol = 1e-6 * np.sqrt(n * t * h)
         for key in ("objective", "primal_residual", "dual_residual", "loss_term"):
-            assert abs(m_g[key] - m_o[key]) <= 2e-4 * abs(m_o[key]) + 1e-7, (s, key, m_g[key], m_o[key])
+            assert abs(m_g[key] - m_o[key]) <= 2e-4 * abs(m_o[key]) + atol, (s, key, m_g[key], m_o[key])
 
 
 def test_scratch_chunking_is_invisible():

@@ -37,6 +37,7 @@ class Problem(C.Structure):
         ("a", C.c_void_p), ("dual_y", C.c_void_p),
         ("wx", C.c_void_p), ("wh", C.c_void_p), ("wy", C.c_void_p),
         ("tc_ws", C.c_void_p), ("tc_ws_bytes", C.c_int64),
+        ("zstore", C.c_void_p), ("wx_prev", C.c_void_p),
     ]
 
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "admm_predict": (C.c_int, [PP, vp, vp, vp]),
     "admm_wy_grad": (C.c_int, [PP, vp, vp]),
     "admm_wy_apply": (C.c_int, [PP, vp, vp]),
+    "admm_weight_begin": (C.c_int, [PP, C.c_int, vp]),
     "admm_weight_grad": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "admm_weight_finish_grad": (C.c_int, [PP, C.c_int, vp, vp, vp]),
     "admm_weight_probe": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp]),

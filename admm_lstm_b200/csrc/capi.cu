@@ -153,6 +153,15 @@ int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream) {
   return launch_wy_apply(*p, g_acc, (cudaStream_t)stream);
 }
 
+int admm_weight_begin(const admm_problem* p, int src, void* stream) {
+  int rc = validate(p, "admm_weight_begin");
+  if (rc) return rc;
+  ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_begin: bad src");
+  if (src == ADMM_SRC_H && p->zstore && p->wx_prev && p->tc_ws && tc_eligible(p))
+    return tc_refresh_wx_delta(p, (cudaStream_t)stream);
+  return ADMM_OK;
+}
+
 int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scratch, double* g_acc,
                      double* fw_acc, void* stream) {
   int rc = validate(p, "admm_weight_grad");
@@ -166,6 +175,11 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   const bool atr_on_tc = use_tc && src == ADMM_SRC_H;
   a.scratch = scratch; a.tc = tc; a.fw_acc = fw_acc; a.src = src;
   a.scratch_q = atr_on_tc ? scratch + 4LL * p->H * tc * p->ldn : nullptr;     // tf32 low part of R^T
+  if (use_tc && p->zstore && p->wx_prev) {
+    // x-phase: full GEMM, z kept; h-phase: z <- z + x (W_new - W_old), no full GEMM
+    a.zstore = p->zstore; a.zT = p->T; a.zt0 = t0;
+    a.z_accumulate = (src == ADMM_SRC_H);
+  }
   rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
   if (rc) return rc;
   AtrArgs r;
@@ -201,11 +215,14 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
   const int64_t half = 4LL * p->H * tc * p->ldn;
   a.tc = tc; a.src = src; a.grad = grad; a.done = done;
   a.scratch = scratch; a.scratch_q = scratch + half;
+  const bool stored = p->tc_ws && tc_eligible(p) && p->zstore && p->wx_prev;
+  if (stored) { a.zstore = p->zstore; a.zT = p->T; a.zt0 = t0; }
   rc = run_gate_gemm(GG_PROBE, p, a, tc, st);
   if (rc) return rc;
   ProbeEvalArgs e;
   e.n = p->n; e.ldn = p->ldn; e.H = p->H; e.tc = tc;
-  e.z0 = a.scratch; e.q = a.scratch_q;
+  e.z0 = stored ? p->zstore : a.scratch; e.q = a.scratch_q;
+  e.z_T = stored ? p->T : tc; e.z_t0 = stored ? t0 : 0;
   for (int g = 0; g < 4; ++g) { e.gate[g] = a.gate[g]; e.dual[g] = a.dual[g]; e.rho[g] = p->hp.rho[g]; }
   e.s_tstride = a.s_tstride;
   e.k0 = k0; e.ncand = ncand; e.done = done; e.fk_acc = fk_acc;
@@ -225,6 +242,11 @@ int admm_weight_select(const admm_problem* p, int src, const float* grad, const 
 int admm_weight_apply(const admm_problem* p, int src, const float* grad, const float* theta, void* stream) {
   int rc = validate(p, "admm_weight_apply");
   if (rc) return rc;
+  if (src == ADMM_SRC_X && p->wx_prev) {
+    if (cudaMemcpyAsync(p->wx_prev, p->wx, sizeof(float) * 4 * p->D * p->H, cudaMemcpyDeviceToDevice,
+                        (cudaStream_t)stream) != cudaSuccess)
+      return check_launch("wx_prev copy");
+  }
   rc = launch_weight_apply(*p, src, grad, theta, (cudaStream_t)stream);
   if (rc) return rc;
   if (p->tc_ws && tc_eligible(p)) return tc_refresh_weights(p, (cudaStream_t)stream);

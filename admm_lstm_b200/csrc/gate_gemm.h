@@ -34,6 +34,9 @@ struct GateGemmArgs {
   const float* grad;     // PROBE: G [4][K][H]
   const int32_t* done;   // PROBE: [4], the launch is skipped on the device when all four are set
   void* tc_ws;           // tensor-core workspace or nullptr
+  float* zstore;         // [4][H][zT][ldn] pre-activation store (tensor-core path) or nullptr
+  int32_t zT, zt0;       // zstore timesteps, first timestep (0-based) of this launch
+  int32_t z_accumulate;  // GRAD: z = zstore + acc (acc = x (W_new - W_old)) instead of z = acc
   float* h_lo;           // slab t of the h - tf32(h) side buffer (tensor-core path) or nullptr
 };
 
@@ -57,7 +60,8 @@ int atr_simt(const AtrArgs& a, cudaStream_t st);
 struct ProbeEvalArgs {
   int64_t n, ldn;
   int32_t H, tc;
-  const float* z0;       // [4][H][tc][ldn]
+  int32_t z_T, z_t0;     // timestep extent / first timestep of z0's layout ([4][H][z_T][ldn]); q is always [4][H][tc][ldn]
+  const float* z0;
   const float* q;
   const float* gate[4];  // gate_g slab of the first timestep of the chunk
   const float* dual[4];

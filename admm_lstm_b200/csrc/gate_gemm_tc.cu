@@ -150,8 +150,10 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
   __shared__ float red[4 * 4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BM;
-  const int j0 = blockIdx.y * JC;
+  // blockIdx.x walks the unit tiles: CTAs that share the same 128 samples (the A tile) are scheduled together, so the
+  // state is streamed from HBM once per launch and re-used from L2; the weights (a few MB) stay L2-resident anyway.
+  const int j0 = blockIdx.x * JC;
+  const int n0 = blockIdx.y * BM;
   const int tl = blockIdx.z;
   const int D = p.D, H = p.H;
   const int nkx = (D + BK - 1) / BK, nkh = (H + BK - 1) / BK, nkb = nkx + nkh;
@@ -245,60 +247,100 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
 
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
+    // The epilogue is latency-bound if each unit waits for its own loads (measured: ~3x the MMA time of a tile):
+    // every batch of EB units first issues ALL its global loads, then computes, then stores, so ~13*EB loads are
+    // in flight per thread.  Loads use the streaming path (each state entry is touched once per launch).
+    constexpr int EB = 4;
+    const float rho_g[4] = {rho.i, rho.f, rho.g, rho.o};
     for (int jb = 0; jb < JC; jb += 8) {
       float z[4][8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld8(t_row + g * JC + jb, z[g]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int j = j0 + jb + e;
-        const int64_t off = soff + (int64_t)j * ldn + n;
+      for (int eb = 0; eb < 8; eb += EB) {
+        int64_t off[EB];
+#pragma unroll
+        for (int e = 0; e < EB; ++e) off[e] = soff + (int64_t)(j0 + jb + eb + e) * ldn + n;
+
         if (MODE == GG_RAWZ) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            p.scratch[(((int64_t)g * H + j) * p.tc + tl) * ldn + n] = z[g][e];
+          for (int e = 0; e < EB; ++e)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              __stcs(p.scratch + (((int64_t)g * H + (j0 + jb + eb + e)) * p.tc + tl) * ldn + n, z[g][eb + e]);
         }
         if (MODE == GG_FORWARD) {
-          const ForwardResult r = forward_point(z[0][e], z[1][e], z[2][e], z[3][e], p.c_prev[off]);
-          if (p.gate[0]) p.gate[0][off] = r.i;
-          if (p.gate[1]) p.gate[1][off] = r.f;
-          if (p.gate[2]) p.gate[2][off] = r.g;
-          if (p.gate[3]) p.gate[3][off] = r.o;
-          p.gate[4][off] = r.c;
-          p.gate[5][off] = r.h;
-          if (p.h_lo) p.h_lo[off] = tf32_lo(r.h);
+          float cp[EB];
+#pragma unroll
+          for (int e = 0; e < EB; ++e) cp[e] = __ldcs(p.c_prev + off[e]);
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
+            const ForwardResult r = forward_point(z[0][eb + e], z[1][eb + e], z[2][eb + e], z[3][eb + e], cp[e]);
+            if (p.gate[0]) __stcs(p.gate[0] + off[e], r.i);
+            if (p.gate[1]) __stcs(p.gate[1] + off[e], r.f);
+            if (p.gate[2]) __stcs(p.gate[2] + off[e], r.g);
+            if (p.gate[3]) __stcs(p.gate[3] + off[e], r.o);
+            __stcs(p.gate[4] + off[e], r.c);
+            p.gate[5][off[e]] = r.h;                         // h_t is the next timestep's A operand: keep it in L2
+            if (p.h_lo) p.h_lo[off[e]] = tf32_lo(r.h);
+          }
         }
         if (MODE == GG_SWEEP) {
-          SweepPoint s;
-          s.zi = z[0][e]; s.zf = z[1][e]; s.zg = z[2][e]; s.zo = z[3][e];
-          s.i = p.gate[0][off]; s.f = p.gate[1][off]; s.g = p.gate[2][off]; s.o = p.gate[3][off];
-          s.c = p.gate[4][off]; s.h = p.gate[5][off]; s.c_prev = p.c_prev[off];
-          s.li = p.dual[0][off]; s.lf = p.dual[1][off]; s.lg = p.dual[2][off]; s.lo = p.dual[3][off];
-          s.lc = p.dual[4][off];
-          s.lh = p.last ? p.dual_h[(int64_t)j * ldn + n] : 0.f;
-          const SweepResult r = sweep_point(s, rho, p.last != 0);
-          p.gate[0][off] = r.i; p.gate[1][off] = r.f; p.gate[2][off] = r.g; p.gate[3][off] = r.o;
-          p.gate[4][off] = r.c;
-          if (!p.last) {
-            p.gate[5][off] = r.h;
-            if (p.h_lo) p.h_lo[off] = tf32_lo(r.h);
+          float in[13][EB];
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) in[q][e] = __ldcs(p.gate[q] + off[e]);
+            in[6][e] = __ldcs(p.c_prev + off[e]);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) in[7 + q][e] = __ldcs(p.dual[q] + off[e]);
+            in[12][e] = p.last ? __ldcs(p.dual_h + (int64_t)(j0 + jb + eb + e) * ldn + n) : 0.f;
           }
-          p.dual[0][off] = r.li; p.dual[1][off] = r.lf; p.dual[2][off] = r.lg; p.dual[3][off] = r.lo;
-          p.dual[4][off] = r.lc;
-          if (ok) { msum[0] += r.prim_sq; msum[1] += r.dual_sq; msum[2] += r.penalty; }
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
+            SweepPoint s;
+            s.zi = z[0][eb + e]; s.zf = z[1][eb + e]; s.zg = z[2][eb + e]; s.zo = z[3][eb + e];
+            s.i = in[0][e]; s.f = in[1][e]; s.g = in[2][e]; s.o = in[3][e]; s.c = in[4][e]; s.h = in[5][e];
+            s.c_prev = in[6][e];
+            s.li = in[7][e]; s.lf = in[8][e]; s.lg = in[9][e]; s.lo = in[10][e]; s.lc = in[11][e]; s.lh = in[12][e];
+            const SweepResult r = sweep_point(s, rho, p.last != 0);
+            __stcs(p.gate[0] + off[e], r.i); __stcs(p.gate[1] + off[e], r.f); __stcs(p.gate[2] + off[e], r.g);
+            __stcs(p.gate[3] + off[e], r.o);
+            p.gate[4][off[e]] = r.c;                         // c_t is read again by the next timestep
+            if (!p.last) {
+              p.gate[5][off[e]] = r.h;
+              if (p.h_lo) p.h_lo[off[e]] = tf32_lo(r.h);
+            }
+            __stcs(p.dual[0] + off[e], r.li); __stcs(p.dual[1] + off[e], r.lf); __stcs(p.dual[2] + off[e], r.lg);
+            __stcs(p.dual[3] + off[e], r.lo); __stcs(p.dual[4] + off[e], r.lc);
+            if (ok) { msum[0] += r.prim_sq; msum[1] += r.dual_sq; msum[2] += r.penalty; }
+          }
         }
         if (MODE == GG_GRAD) {
+          float lam[4][EB], gv[4][EB], zold[4][EB];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float rg = (g == 0) ? rho.i : (g == 1) ? rho.f : (g == 2) ? rho.g : rho.o;
-            float u;
-            const float rr = grad_point(z[g][e], p.dual[g][off], p.gate[g][off], rg, g == 2, &u);
-            const float rv = ok ? rr : 0.f;
-            const int64_t so = (((int64_t)g * H + j) * p.tc + tl) * ldn + n;
-            p.scratch[so] = rv;
-            if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv);
-            if (ok) msum[g] += u * u;
-          }
+          for (int e = 0; e < EB; ++e)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              lam[g][e] = __ldcs(p.dual[g] + off[e]);
+              gv[g][e] = __ldcs(p.gate[g] + off[e]);
+              zold[g][e] = p.z_accumulate
+                  ? __ldcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n) : 0.f;
+            }
+#pragma unroll
+          for (int e = 0; e < EB; ++e)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float u;
+              const float zz = z[g][eb + e] + zold[g][e];
+              if (p.zstore) __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, zz);
+              const float rr = grad_point(zz, lam[g][e], gv[g][e], rho_g[g], g == 2, &u);
+              const float rv = ok ? rr : 0.f;
+              const int64_t so = (((int64_t)g * H + (j0 + jb + eb + e)) * p.tc + tl) * ldn + n;
+              p.scratch[so] = rv;                            // read right back by the A^T R GEMM: keep in L2
+              if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv);
+              if (ok) msum[g] += u * u;
+            }
         }
       }
     }
@@ -416,7 +458,7 @@ struct MapKey {
 std::mutex g_map_mu;
 std::map<MapKey, TcMaps> g_maps;
 
-int get_maps(const admm_problem* p, int src, TcMaps* out) {
+int get_maps(const admm_problem* p, int grad_src, TcMaps* out) {
   std::lock_guard<std::mutex> lk(g_map_mu);
   const MapKey key{p->x, p->gate[5], p->tc_ws, p->ldn, p->T, p->D, p->H};
   auto it = g_maps.find(key);
@@ -442,7 +484,7 @@ int get_maps(const admm_problem* p, int src, TcMaps* out) {
   // the gradient maps depend on src (K = D or H); they are cheap to encode per call
   const WsLayout w = ws_layout(p);
   float* ws = (float*)p->tc_ws;
-  const uint64_t K = (src == ADMM_SRC_X) ? p->D : p->H, H = p->H;
+  const uint64_t K = (grad_src == ADMM_SRC_X) ? p->D : p->H, H = p->H;
   int rc = make_map(&out->gx_hi, ws + w.g_hi, H, K, 4, H, K * H);
   rc |= make_map(&out->gx_lo, ws + w.g_lo, H, K, 4, H, K * H);
   return rc ? ADMM_ECUDA : ADMM_OK;
@@ -457,7 +499,7 @@ int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, 
     cudaFuncSetAttribute(gate_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     configured = true;
   }
-  dim3 grid((unsigned)(p->ldn / BM), (unsigned)(p->H / C::JC), (unsigned)tc);
+  dim3 grid((unsigned)(p->H / C::JC), (unsigned)(p->ldn / BM), (unsigned)tc);
   gate_gemm_tc_kernel<MODE><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a, maps, slab0, rng);
   count_launch();
   return check_launch("gate_gemm_tc");
@@ -502,6 +544,26 @@ int tc_refresh_state(const admm_problem* p, cudaStream_t st) {
   return check_launch("tc_refresh_state");
 }
 
+__global__ void split_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ hi,
+                                  float* __restrict__ lo, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = a[i] - b[i];
+  const float h = tf32_round(v);
+  hi[i] = h;
+  lo[i] = tf32_round(v - h);
+}
+
+// operand slot <- hi/lo split of (x2g - wx_prev): what the h-phase adds to the stored pre-activations
+int tc_refresh_wx_delta(const admm_problem* p, cudaStream_t st) {
+  const WsLayout w = ws_layout(p);
+  float* ws = (float*)p->tc_ws;
+  const int64_t n = 4LL * p->D * p->H;
+  split_diff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->wx, p->wx_prev, ws + w.g_hi, ws + w.g_lo, n);
+  count_launch();
+  return check_launch("tc_refresh_wx_delta");
+}
+
 int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStream_t st) {
   const WsLayout w = ws_layout(p);
   float* ws = (float*)p->tc_ws;
@@ -518,7 +580,9 @@ float* tc_h_lo(const admm_problem* p) {
 int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int tc, cudaStream_t st) {
   GateGemmArgs a = a_in;
   TcMaps maps;
-  int rc = get_maps(p, a.src, &maps);
+  // the "gradient" operand slot holds G of the probed weight, or, for the zstore refresh of the h-phase, W_new - W_old of x2g
+  const bool z_refresh = (mode == GG_GRAD && a.z_accumulate);
+  int rc = get_maps(p, z_refresh ? ADMM_SRC_X : a.src, &maps);
   if (rc) return rc;
   // slab index of h_{t-1} / x_t of the first timestep in the launch
   const int64_t slab_elems = (int64_t)p->H * p->ldn;
@@ -529,13 +593,17 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   switch (mode) {
     case GG_FORWARD: return launch_tc<GG_FORWARD>(p, a, maps, slab0, tc, full, st);
     case GG_SWEEP: return launch_tc<GG_SWEEP>(p, a, maps, slab0, tc, full, st);
-    case GG_GRAD: return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, full, st);
+    case GG_GRAD:
+      if (z_refresh) return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, TcRange{0, nkx, 1}, st);
+      return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, full, st);
     case GG_RAWZ: return launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st);
     case GG_PROBE: {
       // Z0 = x W + h U, then Q = A_src G: two launches of the same kernel (each keeps the 64-unit tile and
       // two resident CTAs per SM; a fused Z0|Q tile needs all 512 TMEM columns and halves the tile width)
-      rc = launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st);
-      if (rc) return rc;
+      if (!a.zstore) {
+        rc = launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st);
+        if (rc) return rc;
+      }
       GateGemmArgs q = a;
       q.scratch = a.scratch_q;
       const TcRange qr = (a.src == ADMM_SRC_X) ? TcRange{0, nkx, 1} : TcRange{nkx, nkx + nkh, 1};

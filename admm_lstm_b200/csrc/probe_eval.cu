@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
         const int j = j0 + jj;
         if (j >= p.H) break;
         const int64_t so = (((int64_t)g * p.H + j) * p.tc + tl) * p.ldn + n;
-        const float4 z4 = ld_stream(p.z0 + so), q4 = ld_stream(p.q + so);
+        const int64_t zo = (((int64_t)g * p.H + j) * p.z_T + p.z_t0 + tl) * p.ldn + n;
+        const float4 z4 = ld_stream(p.z0 + zo), q4 = ld_stream(p.q + so);
         const float4 lam4 = ld_stream(dual + (int64_t)j * p.ldn), gv4 = ld_stream(gate + (int64_t)j * p.ldn);
         if (g == 2) accumulate<NC, true>(z4, q4, lam4, gv4, rho, inv_theta, ok, acc);
         else accumulate<NC, false>(z4, q4, lam4, gv4, rho, inv_theta, ok, acc);

@@ -12,6 +12,7 @@ int tc_refresh_weights(const admm_problem* p, cudaStream_t st);
 int tc_refresh_inputs(const admm_problem* p, cudaStream_t st);
 int tc_refresh_state(const admm_problem* p, cudaStream_t st);
 int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStream_t st);
+int tc_refresh_wx_delta(const admm_problem* p, cudaStream_t st);
 int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st);
 int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st);
 float* tc_h_lo(const admm_problem* p);

@@ -103,7 +103,7 @@ class ADMMBasedOptimizer(object):
                  parameter_dictionary: Optional[Dict[str, Dict[str, float]]] = None, verbose: bool = True, *,
                  variant: Optional[str] = None, with_dual_y: bool = False, sharding: str = "slice",
                  use_tensor_cores: Optional[bool] = None, scratch_bytes: Optional[int] = None,
-                 comm: Optional[Comm] = None) -> None:
+                 comm: Optional[Comm] = None, keep_preactivations: Optional[bool] = None) -> None:
         self._lib = _lib.load()
         self.device = _require_cuda()
         if self._lib.admm_device_ok() <= 0:
@@ -205,6 +205,17 @@ class ADMMBasedOptimizer(object):
             p.tc_ws, p.tc_ws_bytes = self._tc_ws.data_ptr(), ws_bytes
             self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS | _lib.TC_INPUTS, _stream_ptr())
         self.uses_tensor_cores = want_tc
+        # pre-activation store: 4 state tensors' worth of memory buys 3 of the 7 full-size GEMM passes per step
+        self._zstore = self._wx_prev = None
+        z_bytes = 16 * H * T * self.ldn
+        if keep_preactivations is None:
+            free, _ = torch.cuda.mem_get_info(dev)
+            keep_preactivations = want_tc and z_bytes < 0.6 * free
+        if keep_preactivations and want_tc:
+            self._zstore = torch.empty(4 * H * T * self.ldn, dtype=f32, device=dev)
+            self._wx_prev = self._wx.clone()
+            p.zstore, p.wx_prev = self._zstore.data_ptr(), self._wx_prev.data_ptr()
+        self.keeps_preactivations = self._zstore is not None
 
         self.gates = _StateDict({**{k: (lambda k=k: self._state[k].permute(2, 0, 1)[:N]) for k in _STATE_KEYS},
                                  "a": lambda: self._a.t()[:N]})
@@ -441,6 +452,7 @@ class ADMMBasedOptimizer(object):
         acc.zero_()
         g_ptr, fw_ptr = acc.data_ptr(), acc[n_g:].data_ptr()
         chunks = self._time_chunks()
+        self._call("admm_weight_begin", pp, src, st)
         for t0, tc in chunks:
             self._call("admm_weight_grad", pp, src, t0, tc, self._scratch.data_ptr(), g_ptr, fw_ptr, st)
         self.comm.allreduce_sum_(acc)

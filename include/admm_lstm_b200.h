@@ -78,6 +78,12 @@ typedef struct admm_problem {
    * by the caller before first use. */
   void* tc_ws;
   int64_t tc_ws_bytes;
+  /* Optional (tensor-core path only; NULL -> the pre-activations are recomputed in every pass):
+   * zstore [4][H][T][ldn] keeps z = x W + h U of all timesteps between the passes of the weight phase, so the
+   * phase needs 4 instead of 7 full-size GEMM passes per step; wx_prev [4][D][H] is the copy of
+   * x2g taken before its update, from which the h-phase refreshes zstore with x (W_new - W_old) only. */
+  float* zstore;
+  float* wx_prev;
 } admm_problem;
 
 /* Slots of the fp64 metric accumulator filled by admm_sweep_t / admm_last_apply. */
@@ -123,6 +129,8 @@ int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream);
  *           admm.py:338) and done[g].  fw_acc (from grad) is kept for reporting only.
  *  apply  : w <- (0.5 rho T theta w - G)/(beta + 0.5 rho theta T)           (admm.py:340-343)
  * K = D for ADMM_SRC_X, H for ADMM_SRC_H. */
+/* begin: once per `src` before the first admm_weight_grad of the phase (prepares the zstore refresh operands). */
+int admm_weight_begin(const admm_problem* p, int src, void* stream);
 int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scratch,
                      double* g_acc, double* fw_acc, void* stream);
 int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out,

@@ -193,22 +193,36 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   return atr_simt(r, st);
 }
 
-int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out, void* stream) {
+int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out, double* est_acc,
+                            void* stream) {
   int rc = validate(p, "admm_weight_finish_grad");
   if (rc) return rc;
+  ADMM_REQUIRE(g_acc && grad_out && est_acc, "admm_weight_finish_grad: null buffers");
   rc = launch_weight_finish(*p, src, g_acc, grad_out, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = launch_weight_est(*p, src, grad_out, est_acc, (cudaStream_t)stream);
   if (rc) return rc;
   if (p->tc_ws && tc_eligible(p)) return tc_refresh_grad(p, src, grad_out, (cudaStream_t)stream);
   return ADMM_OK;
 }
 
-int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scratch, const float* grad, int k0,
-                      int ncand, const int32_t* done, double* fk_acc, void* stream) {
+static int check_plan(const admm_probe_plan* plan, const char* who) {
+  ADMM_REQUIRE(plan, "%s: null plan", who);
+  ADMM_REQUIRE(plan->ncand >= 1 && plan->ncand <= ADMM_MAX_CAND, "%s: bad ncand %d", who, plan->ncand);
+  for (int g = 0; g < 4; ++g) {
+    ADMM_REQUIRE(plan->k0[g] >= 0 && plan->k0[g] + plan->ncand <= ADMM_EST_CAND, "%s: bad k0[%d]=%d", who, g, plan->k0[g]);
+    ADMM_REQUIRE(!plan->proof || plan->k0[g] <= ADMM_MAX_CAND, "%s: proof range too long", who);
+  }
+  return ADMM_OK;
+}
+
+int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scratch, const float* grad,
+                      const admm_probe_plan* plan, const int32_t* done, double* fk_acc, void* stream) {
   int rc = validate(p, "admm_weight_probe");
   if (rc) return rc;
   ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_probe: bad src");
   ADMM_REQUIRE(t0 >= 0 && tc >= 1 && t0 + tc <= p->T, "admm_weight_probe: bad timestep range");
-  ADMM_REQUIRE(ncand >= 1 && ncand <= ADMM_MAX_CAND && k0 >= 0 && k0 + ncand <= 120, "admm_weight_probe: bad candidates");
+  if ((rc = check_plan(plan, "admm_weight_probe"))) return rc;
   ADMM_REQUIRE(scratch && grad && done && fk_acc, "admm_weight_probe: null buffers");
   cudaStream_t st = (cudaStream_t)stream;
   GateGemmArgs a = base_args(p, t0 + 1);
@@ -225,18 +239,22 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
   e.z_T = stored ? p->T : tc; e.z_t0 = stored ? t0 : 0;
   for (int g = 0; g < 4; ++g) { e.gate[g] = a.gate[g]; e.dual[g] = a.dual[g]; e.rho[g] = p->hp.rho[g]; }
   e.s_tstride = a.s_tstride;
-  e.k0 = k0; e.ncand = ncand; e.done = done; e.fk_acc = fk_acc;
+  for (int g = 0; g < 4; ++g) e.k0[g] = plan->k0[g];
+  e.ncand = plan->ncand; e.proof = 0; e.done = done; e.fk_acc = fk_acc;
+  rc = probe_eval(e, st);
+  if (rc || !plan->proof) return rc;
+  e.proof = 1;
   return probe_eval(e, st);
 }
 
-int admm_weight_select(const admm_problem* p, int src, const float* grad, const double* fw_acc,
-                       const double* fk_acc, int k0, int ncand, int final_pass, int32_t* done, float* theta_out,
-                       void* stream) {
+int admm_weight_select(const admm_problem* p, int src, const double* est_acc, const double* fk_acc,
+                       const admm_probe_plan* plan, int final_pass, int32_t* done, float* theta_out, void* stream) {
   int rc = validate(p, "admm_weight_select");
   if (rc) return rc;
-  ADMM_REQUIRE(ncand >= 1 && ncand <= ADMM_MAX_CAND, "admm_weight_select: bad ncand");
-  return launch_weight_select(*p, src, grad, fw_acc, fk_acc, k0, ncand, final_pass, done, theta_out,
-                              (cudaStream_t)stream);
+  (void)src;
+  if ((rc = check_plan(plan, "admm_weight_select"))) return rc;
+  ADMM_REQUIRE(est_acc && fk_acc && done && theta_out, "admm_weight_select: null buffers");
+  return launch_weight_select(*p, est_acc, fk_acc, *plan, final_pass, done, theta_out, (cudaStream_t)stream);
 }
 
 int admm_weight_apply(const admm_problem* p, int src, const float* grad, const float* theta, void* stream) {

@@ -55,8 +55,8 @@ struct AtrArgs {
 };
 int atr_simt(const AtrArgs& a, cudaStream_t st);
 
-// fk_acc[4][ADMM_MAX_CAND + 1] (fp64) += sum over the chunk of (act(Z0 + Q 2^-(k0+k)) - lambda/rho - gate)^2 for
-// k < ncand, and, in the last slot of each gate, the same sum at Q = 0, i.e. f(w)   (admm.py:316-325).
+// fk_acc[4][ADMM_FK_SLOTS] (fp64) += sum over the chunk of (act(Z0 + Q 2^-k) - lambda/rho - gate)^2 for the thetas
+// of the plan, and, in slot 32 of each gate, the same sum at Q = 0, i.e. f(w)   (admm.py:316-325).
 struct ProbeEvalArgs {
   int64_t n, ldn;
   int32_t H, tc;
@@ -67,9 +67,11 @@ struct ProbeEvalArgs {
   const float* dual[4];
   int64_t s_tstride;
   float rho[4];
-  int32_t k0, ncand;
+  int32_t k0[4];         // first theta exponent of the window, per gate
+  int32_t ncand;         // window size
+  int32_t proof;         // 1: evaluate k < k0[g] on one unit block in PROOF_STRIDE (lower bounds) instead of the window
   const int32_t* done;
-  double* fk_acc;
+  double* fk_acc;        // [4][ADMM_FK_SLOTS]
 };
 int probe_eval(const ProbeEvalArgs& a, cudaStream_t st);
 

@@ -22,7 +22,8 @@ namespace {
 
 constexpr int NT = 256;
 constexpr int JB = 8;          // hidden units per block
-constexpr int NCS = ADMM_MAX_CAND + 1;
+constexpr int NCS = ADMM_FK_SLOTS;
+constexpr int PROOF_STRIDE = 8;   // lower-bound sums use one block of JB units in PROOF_STRIDE
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -81,17 +82,22 @@ template <int NC>
 __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, int n_jb, int n_nb, int64_t n_items) {
   __shared__ float red[(NC + 1) * (NT / 32)];
   if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
-  float inv_theta[NC];
-#pragma unroll
-  for (int k = 0; k < NC; ++k) inv_theta[k] = (k < p.ncand) ? ldexpf(1.0f, -(p.k0 + k)) : 0.f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jstep = p.proof ? PROOF_STRIDE : 1;
 
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int nb = (int)(item % n_nb);
-    const int jb = (int)((item / n_nb) % n_jb);
+    const int jb = (int)((item / n_nb) % n_jb) * jstep;
     const int gt = (int)(item / ((int64_t)n_nb * n_jb));
     const int g = gt & 3, tl = gt >> 2;
     if (p.done[g]) continue;
+    // window: theta = 2^(k0[g]+k), k < ncand ; proof: theta = 2^k, k < k0[g]
+    const int kbase = p.proof ? 0 : p.k0[g];
+    const int nc = p.proof ? p.k0[g] : p.ncand;
+    if (nc <= 0) continue;
+    float inv_theta[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) inv_theta[k] = (k < nc) ? ldexpf(1.0f, -(kbase + k)) : 0.f;
     const int64_t n = ((int64_t)nb * NT + threadIdx.x) * 4;
     const int j0 = jb * JB;
     float acc[NC + 1];
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
         else accumulate<NC, false>(z4, q4, lam4, gv4, rho, inv_theta, ok, acc);
       }
     }
-    // candidates beyond ncand were evaluated at Q*0 (= f(w)); only slots < ncand and the f(w) slot are published
+    // slots beyond nc were evaluated at Q*0 (= f(w)); only slots < nc and, for the window, the f(w) slot are published
 #pragma unroll
     for (int k = 0; k <= NC; ++k) {
       const float s = warp_sum(acc[k]);
@@ -123,10 +129,11 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
     __syncthreads();
     if (threadIdx.x <= NC) {
       const int k = threadIdx.x;
-      if (k < p.ncand || k == NC) {
+      if (k < nc || (k == NC && !p.proof)) {
         double s = 0.0;
         for (int w = 0; w < NT / 32; ++w) s += (double)red[k * (NT / 32) + w];
-        atomicAdd(p.fk_acc + g * NCS + (k == NC ? ADMM_MAX_CAND : k), s);
+        const int slot = (k == NC) ? ADMM_MAX_CAND : (p.proof ? ADMM_MAX_CAND + 1 + k : k);
+        atomicAdd(p.fk_acc + g * NCS + slot, s);
       }
     }
     __syncthreads();
@@ -136,11 +143,18 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
 }  // namespace
 
 int probe_eval(const ProbeEvalArgs& a, cudaStream_t st) {
-  const int n_nb = (int)((a.ldn / 4 + NT - 1) / NT), n_jb = (a.H + JB - 1) / JB;
+  const int n_nb = (int)((a.ldn / 4 + NT - 1) / NT);
+  int n_jb = (a.H + JB - 1) / JB;
+  int nc = a.ncand;
+  if (a.proof) {
+    n_jb = (n_jb + PROOF_STRIDE - 1) / PROOF_STRIDE;
+    nc = max(max(a.k0[0], a.k0[1]), max(a.k0[2], a.k0[3]));
+    if (nc <= 0) return ADMM_OK;
+  }
   const int64_t n_items = (int64_t)n_nb * n_jb * 4 * a.tc;
   const unsigned grid = (unsigned)(n_items < 148 * 8 ? n_items : 148 * 8);
-  if (a.ncand <= 8) probe_eval_kernel<8><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
-  else if (a.ncand <= 16) probe_eval_kernel<16><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
+  if (nc <= 8) probe_eval_kernel<8><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
+  else if (nc <= 16) probe_eval_kernel<16><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
   else probe_eval_kernel<ADMM_MAX_CAND><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
   count_launch();
   return check_launch("probe_eval");

@@ -282,28 +282,23 @@ __global__ void weight_finish_kernel(const double* g_acc, float* grad, const adm
   grad[idx] = (float)g_acc[idx] * hp.rho[g];          // admm.py:312
 }
 
-// One CTA per gate.  Replays admm.py:331-338 for theta_k = 2^(k0+k): beta_k = w + G/theta_k (fp32, as the
-// reference rounds it), est_k = f(w) + <G, beta_k - w> + T*0.5*theta_k*||beta_k - w||^2, exit at the first k
-// with !(f(beta_k) > est_k).
-template <int NC>
-__global__ void __launch_bounds__(256) weight_select_kernel(const float* w_all, const float* grad_all,
-                                                            const double* fw_acc, const double* fk_acc,
-                                                            admm_hyper hp, int T, int64_t per_gate, int k0, int ncand,
-                                                            int final_pass, int32_t* done, float* theta_out) {
-  __shared__ double red[2 * NC][8];
-  __shared__ double tot[2 * NC];
-  const int g = blockIdx.x;
-  if (done[g]) return;
+// est() ingredients for every theta = 2^k, k < ADMM_EST_CAND, once per weight update (w and G do not change between
+// probe passes):  s1_k = <G, beta_k - w>, s2_k = ||beta_k - w||^2 with beta_k = fl(w + G/2^k) rounded to fp32 exactly
+// as the reference forms it (admm.py:332,336).  grid = (4 gates, ADMM_EST_CAND/8 candidate groups, element blocks).
+__global__ void __launch_bounds__(256) weight_est_kernel(const float* w_all, const float* grad_all, int64_t per_gate,
+                                                         double* est_acc) {
+  __shared__ double red[16][8];
+  const int g = blockIdx.x, kg = blockIdx.y * 8;
   const float* w = w_all + (int64_t)g * per_gate;
   const float* G = grad_all + (int64_t)g * per_gate;
-  double s1[NC], s2[NC];
+  double s1[8], s2[8];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
-  for (int64_t e = threadIdx.x; e < per_gate; e += blockDim.x) {
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
+  for (int64_t e = (int64_t)blockIdx.z * blockDim.x + threadIdx.x; e < per_gate; e += (int64_t)gridDim.z * blockDim.x) {
     const float wv = w[e], gv = G[e];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const float beta = wv + gv * ldexpf(1.0f, -(k0 + k));      // G / 2^k is exact
+    for (int k = 0; k < 8; ++k) {
+      const float beta = wv + gv * ldexpf(1.0f, -(kg + k));      // G / 2^k is exact
       const float d = beta - wv;
       s1[k] += (double)(gv * d);
       s2[k] += (double)(d * d);
@@ -311,35 +306,54 @@ __global__ void __launch_bounds__(256) weight_select_kernel(const float* w_all, 
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NC; ++k) {
+  for (int k = 0; k < 8; ++k) {
     const double a = warp_sum(s1[k]), b = warp_sum(s2[k]);
-    if (lane == 0) { red[k][warp] = a; red[NC + k][warp] = b; }
+    if (lane == 0) { red[k][warp] = a; red[8 + k][warp] = b; }
   }
   __syncthreads();
-  if (threadIdx.x < 2 * NC) {
+  if (threadIdx.x < 16) {
     double s = 0.0;
     for (int q = 0; q < 8; ++q) s += red[threadIdx.x][q];
-    tot[threadIdx.x] = s;
+    const int k = kg + (threadIdx.x & 7), which = threadIdx.x >> 3;
+    atomicAdd(est_acc + ((int64_t)g * ADMM_EST_CAND + k) * 2 + which, s);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const float rho = hp.rho[g];
-    (void)fw_acc;
-    const float f_w = 0.5f * rho * (float)fk_acc[g * (ADMM_MAX_CAND + 1) + ADMM_MAX_CAND];
-    int found = -1;
-    for (int k = 0; k < ncand; ++k) {
-      const float theta = ldexpf(1.0f, k0 + k);
-      const float f_b = 0.5f * rho * (float)fk_acc[g * (ADMM_MAX_CAND + 1) + k];
-      const float est = f_w + (float)tot[k] + ((float)T * 0.5f * theta) * (float)tot[NC + k];
-      if (!(f_b > est)) { found = k; break; }
+}
+
+// Replays admm.py:331-338 per gate from the reduced sums: theta_k = 2^k, est_k = f(w) + s1_k + T*0.5*theta_k*s2_k, exit at
+// the first k with !(f(beta_k) > est_k).  With plan.proof the candidates below the window are represented by
+// lower bounds of f(beta_k): "bound > est_k" proves the loop continues; an unproven k leaves the gate undecided.
+__global__ void weight_select_kernel(const double* est_acc, const double* fk_acc, admm_hyper hp, int T,
+                                     admm_probe_plan plan, int final_pass, int32_t* done, float* theta_out) {
+  const int g = threadIdx.x;
+  if (g >= 4 || done[g]) return;
+  const float rho = hp.rho[g];
+  const double* fk = fk_acc + g * ADMM_FK_SLOTS;
+  const double* es = est_acc + (int64_t)g * ADMM_EST_CAND * 2;
+  const float f_w = 0.5f * rho * (float)fk[ADMM_MAX_CAND];
+  auto est = [&](int k) {
+    const float theta = ldexpf(1.0f, k);
+    return f_w + (float)es[2 * k] + ((float)T * 0.5f * theta) * (float)es[2 * k + 1];
+  };
+  const int k0 = plan.k0[g];
+  if (plan.proof) {
+    for (int k = 0; k < k0; ++k) {
+      const float lower = 0.5f * rho * (float)fk[ADMM_MAX_CAND + 1 + k];
+      if (!(lower > est(k))) return;                 // not provable from the subsample: a full pass will decide
     }
-    if (found >= 0) {
-      theta_out[g] = ldexpf(1.0f, k0 + found - 1);     // theta /= 2 (admm.py:338)
-      done[g] = 1;
-    } else if (final_pass) {
-      theta_out[g] = ldexpf(1.0f, k0 + ncand - 1);     // iteration cap (the reference has none)
-      done[g] = 1;
-    }
+  }
+  int found = -1;
+  for (int c = 0; c < plan.ncand; ++c) {
+    const int k = k0 + c;
+    if (k >= ADMM_EST_CAND) break;
+    const float f_b = 0.5f * rho * (float)fk[c];
+    if (!(f_b > est(k))) { found = k; break; }
+  }
+  if (found >= 0) {
+    theta_out[g] = ldexpf(1.0f, found - 1);            // theta /= 2 (admm.py:338)
+    done[g] = 1;
+  } else if (final_pass) {
+    theta_out[g] = ldexpf(1.0f, k0 + plan.ncand - 1);  // iteration cap (the reference has none)
+    done[g] = 1;
   }
 }
 
@@ -397,20 +411,19 @@ int launch_weight_finish(const admm_problem& p, int src, const double* g_acc, fl
   count_launch();
   return check_launch("weight_finish");
 }
-int launch_weight_select(const admm_problem& p, int src, const float* grad, const double* fw_acc,
-                         const double* fk_acc, int k0, int ncand, int final_pass, int32_t* done, float* theta,
-                         cudaStream_t st) {
+int launch_weight_est(const admm_problem& p, int src, const float* grad, double* est_acc, cudaStream_t st) {
   const int64_t per_gate = (int64_t)(src == ADMM_SRC_X ? p.D : p.H) * p.H;
   const float* w = (src == ADMM_SRC_X) ? p.wx : p.wh;
-  if (ncand <= 8)
-    weight_select_kernel<8><<<4, 256, 0, st>>>(w, grad, fw_acc, fk_acc, p.hp, p.T, per_gate, k0, ncand, final_pass,
-                                               done, theta);
-  else if (ncand <= 16)
-    weight_select_kernel<16><<<4, 256, 0, st>>>(w, grad, fw_acc, fk_acc, p.hp, p.T, per_gate, k0, ncand, final_pass,
-                                                done, theta);
-  else
-    weight_select_kernel<ADMM_MAX_CAND><<<4, 256, 0, st>>>(w, grad, fw_acc, fk_acc, p.hp, p.T, per_gate, k0, ncand,
-                                                           final_pass, done, theta);
+  if (cudaMemsetAsync(est_acc, 0, sizeof(double) * 4 * ADMM_EST_CAND * 2, st) != cudaSuccess) return check_launch("est memset");
+  const unsigned nz = (unsigned)((per_gate + 256 * 64 - 1) / (256 * 64));
+  dim3 grid(4, ADMM_EST_CAND / 8, nz < 1 ? 1 : (nz > 32 ? 32 : nz));
+  weight_est_kernel<<<grid, 256, 0, st>>>(w, grad, per_gate, est_acc);
+  count_launch();
+  return check_launch("weight_est");
+}
+int launch_weight_select(const admm_problem& p, const double* est_acc, const double* fk_acc, const admm_probe_plan& plan,
+                         int final_pass, int32_t* done, float* theta, cudaStream_t st) {
+  weight_select_kernel<<<1, 32, 0, st>>>(est_acc, fk_acc, p.hp, p.T, plan, final_pass, done, theta);
   count_launch();
   return check_launch("weight_select");
 }

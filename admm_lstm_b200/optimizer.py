@@ -160,7 +160,8 @@ class ADMMBasedOptimizer(object):
         kmax = max(D, H)
         self._acc_wy = torch.zeros(H * O, dtype=torch.float64, device=dev)
         self._acc_grad = torch.zeros(4 * kmax * H + 4, dtype=torch.float64, device=dev)   # [G_acc | f(w)]
-        self._acc_fk = torch.zeros(4 * (_lib.ADMM_MAX_CAND + 1), dtype=torch.float64, device=dev)
+        self._acc_fk = torch.zeros(4 * _lib.ADMM_FK_SLOTS, dtype=torch.float64, device=dev)
+        self._acc_est = torch.zeros(4 * _lib.ADMM_EST_CAND * 2, dtype=torch.float64, device=dev)
         self._acc_last = torch.zeros(1 + 3 * 4, dtype=torch.float64, device=dev)
         self._metrics = torch.zeros(_lib.ADMM_N_METRICS, dtype=torch.float64, device=dev)
         self._grad = torch.zeros(4 * kmax * H, dtype=f32, device=dev)
@@ -171,7 +172,7 @@ class ADMMBasedOptimizer(object):
         # by the launch queue), so the hint for step s usually comes from step s-2
         self._theta_ring = [[torch.zeros(9, dtype=f32).pin_memory(), None, -1] for _ in range(4)]
         self._step_index = 0
-        self._first_cand = {_lib.SRC_X: _lib.ADMM_MAX_CAND, _lib.SRC_H: _lib.ADMM_MAX_CAND}
+        self._hint = None            # per src: exit exponents of step s-2 (list of 4) or None
 
         # scratch of the weight phase: R^T for the gradient pass, Z0 and Q for the probe pass -> 8*H*ldn floats
         # per timestep of a chunk
@@ -381,7 +382,7 @@ class ADMMBasedOptimizer(object):
         return [(t0, min(tc, T - t0)) for t0 in range(0, T, tc)]
 
     def _poll_theta_hint(self) -> None:
-        """Size the first probe pass of step s from the thetas chosen in step s-2.
+        """Fetch the thetas chosen in step s-2: they size the first probe pass of step s.
 
         The schedule must be identical on every rank (the per-pass candidate sums are all-reduced), so it may
         only depend on replicated data, never on timing: the thetas are replicated, and "step s-2" is a fixed
@@ -390,16 +391,28 @@ class ADMMBasedOptimizer(object):
         want = self._step_index - 2
         slot = self._theta_ring[want % len(self._theta_ring)] if want >= 0 else None
         if slot is None or slot[2] != want:
-            self._first_cand = {_lib.SRC_X: _lib.ADMM_MAX_CAND, _lib.SRC_H: _lib.ADMM_MAX_CAND}
+            self._hint = None
             return
         slot[1].synchronize()
         th = slot[0][:8].view(2, 4)
-        for src in (_lib.SRC_X, _lib.SRC_H):
-            kmax = float(th[src].max())
-            # theta_out = 2^(k-1) for exit index k: a first pass of C candidates covers k <= C-1; keep 2 spare, so
-            # that the next step almost always needs a single GEMM pass
-            need = (int(kmax).bit_length() + 3) if kmax >= 1.0 else 3
-            self._first_cand[src] = 8 if need <= 8 else 16 if need <= 16 else _lib.ADMM_MAX_CAND
+        # theta_out = 2^(k-1) for exit index k (0.5 -> k = 0)
+        self._hint = {src: [int(v).bit_length() if v >= 1.0 else 0 for v in th[src].tolist()]
+                      for src in (_lib.SRC_X, _lib.SRC_H)}
+
+    def _probe_plans(self, src: int):
+        """First pass: a window of candidates around the previous exit index of each gate, everything below the
+        window represented by lower-bound sums on 1/8 of the units (admm_probe_plan); then full passes from 0.
+        Window = [k* - 5, k* + 2]: the bound proves `f > est` only with a margin of 8x, which the quadratic growth of
+        f along the step gives ~4 doublings below the exit."""
+        full = [((0, 0, 0, 0), _lib.ADMM_MAX_CAND, 0), ((32, 32, 32, 32), _lib.ADMM_MAX_CAND, 0)]
+        if self._hint is None:
+            return full
+        ks = self._hint[src]
+        k0 = [max(0, min(k - 5, _lib.ADMM_MAX_CAND)) for k in ks]
+        span = max(k + 3 - a for k, a in zip(ks, k0))
+        ncand = min(_lib.ADMM_MAX_CAND, max(8, -(-span // 8) * 8))
+        first = (tuple(k0), ncand, int(any(k0)))
+        return [first] + full
 
     def _push_theta_hint(self) -> None:
         slot = self._theta_ring[self._step_index % len(self._theta_ring)]
@@ -456,19 +469,22 @@ class ADMMBasedOptimizer(object):
         for t0, tc in chunks:
             self._call("admm_weight_grad", pp, src, t0, tc, self._scratch.data_ptr(), g_ptr, fw_ptr, st)
         self.comm.allreduce_sum_(acc)
-        self._call("admm_weight_finish_grad", pp, src, g_ptr, self._grad.data_ptr(), st)
+        self._call("admm_weight_finish_grad", pp, src, g_ptr, self._grad.data_ptr(), self._acc_est.data_ptr(), st)
         self._done.zero_()
         theta_ptr = self._theta_w[4 * src:].data_ptr()
-        first = self._first_cand[src]
-        passes = [(0, first)] + [(first + _lib.ADMM_MAX_CAND * q, _lib.ADMM_MAX_CAND) for q in range(2)]
-        for q, (k0, ncand) in enumerate(passes):
+        plans = self._probe_plans(src)
+        for q, (k0, ncand, proof) in enumerate(plans):
+            plan = _lib.ProbePlan()
+            for g in range(4):
+                plan.k0[g] = k0[g]
+            plan.ncand, plan.proof = ncand, proof
             self._acc_fk.zero_()
             for t0, tc in chunks:
-                self._call("admm_weight_probe", pp, src, t0, tc, self._scratch.data_ptr(), self._grad.data_ptr(), k0, ncand,
-                           self._done.data_ptr(), self._acc_fk.data_ptr(), st)
+                self._call("admm_weight_probe", pp, src, t0, tc, self._scratch.data_ptr(), self._grad.data_ptr(),
+                           C.byref(plan), self._done.data_ptr(), self._acc_fk.data_ptr(), st)
             self.comm.allreduce_sum_(self._acc_fk)
-            self._call("admm_weight_select", pp, src, self._grad.data_ptr(), fw_ptr, self._acc_fk.data_ptr(),
-                       k0, ncand, int(q == len(passes) - 1), self._done.data_ptr(), theta_ptr, st)
+            self._call("admm_weight_select", pp, src, self._acc_est.data_ptr(), self._acc_fk.data_ptr(), C.byref(plan),
+                       int(q == len(plans) - 1), self._done.data_ptr(), theta_ptr, st)
         self._call("admm_weight_apply", pp, src, self._grad.data_ptr(), theta_ptr, st)
 
     def __update_last(self, st) -> None:

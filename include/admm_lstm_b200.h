@@ -42,7 +42,9 @@ extern "C" {
 #define ADMM_SRC_H 1  /* map_from == 'h' : U  = h2g [H,H] */
 
 #define ADMM_MAX_O 16         /* output_size limit of the t = T kernels */
-#define ADMM_MAX_CAND 32      /* theta candidates per probe pass        */
+#define ADMM_MAX_CAND 32      /* theta candidates per probe pass                                   */
+#define ADMM_EST_CAND 64      /* est() sums are precomputed for theta = 2^0 .. 2^63                 */
+#define ADMM_FK_SLOTS 65      /* [0,32) window candidates, [32] f(w), [33,65) lower-bound sums k<32 */
 #define ADMM_N_METRICS 8
 
 /* rho / beta in the reference's own key order (admm.py:131-160, parameters.py). */
@@ -52,6 +54,18 @@ typedef struct admm_hyper {
   float beta_h[4]; /* vi vf vg vo  (h2g) */
   float beta_wy;
 } admm_hyper;
+
+/* Which thetas a probe pass evaluates, per gate (identical on every rank: derived from replicated data).
+ * Window: theta = 2^(k0[g]+c), c < ncand, summed over ALL units -> fk_acc[g][c]; f(w) -> fk_acc[g][32].
+ * proof != 0: additionally, for k < k0[g], the same sum over one unit block in eight -> fk_acc[g][33+k].  A
+ * partial sum of squares is a rigorous LOWER bound of f(w + G/2^k); if even the bound exceeds est_k the
+ * reference's loop provably continues past k (admm.py:334) without the full evaluation.  If a bound does
+ * not prove it, the pass stays undecided for that gate and a full pass from k = 0 follows. */
+typedef struct admm_probe_plan {
+  int32_t k0[4];
+  int32_t ncand;
+  int32_t proof;
+} admm_probe_plan;
 
 /* One rank's shard of the problem.  The optimizer owns every buffer (allocated by the host
  * language -- torch here); this struct only borrows them for the duration of a call. */
@@ -119,14 +133,15 @@ int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream);
  *  grad   : for timesteps t0 < t <= t0+tc: z = x_t W + h_{t-1} U; R = (act z - lambda/rho - gate) act'(z);
  *           g_acc[4][K][H] (fp64) += A_src^T R;  fw_acc[4] (fp64) += sum (act z - lambda/rho - gate)^2.
  *           scratch: 8*H*tc*ldn floats (R^T and, on the tensor-core path, its tf32 low part).
- *  finish : G = rho_g * (float) g_acc  -> grad_out [4][K][H] fp32           (admm.py:312)
- *  probe  : fk_acc[4][ADMM_MAX_CAND+1] (fp64) += sum (act(z + (A_src G)/theta_k) - lambda/rho - gate)^2 for
- *           theta_k = 2^(k0+k), k < ncand, and in slot ADMM_MAX_CAND the same sum at G = 0, i.e. f(w);
+ *  finish : G = rho_g * (float) g_acc  -> grad_out [4][K][H] fp32           (admm.py:312); also est_acc
+ *           [4][ADMM_EST_CAND][2] (fp64) = <G, beta_k - w>, ||beta_k - w||^2 for beta_k = fl(w + G/2^k) (admm.py:327-332)
+ *  probe  : fk_acc[4][ADMM_FK_SLOTS] (fp64) += sum (act(z + (A_src G)/theta) - lambda/rho - gate)^2 for the
+ *           thetas of `plan` (see admm_probe_plan) and, in slot 32, the same sum at G = 0, i.e. f(w);
  *           gates with done[g] != 0 are skipped (admm.py:316-325, 331-336).  scratch: 8*H*tc*ldn floats.
  *  select : per gate, replays `while f(beta) > est(beta, theta): theta *= 2` (admm.py:331-338) over the
- *           candidates k0..k0+ncand-1 from the reduced sums (f(w) is taken from fk_acc's last slot, so both
- *           sides of the comparison come from the same kernel); writes theta_out[g] (already halved,
- *           admm.py:338) and done[g].  fw_acc (from grad) is kept for reporting only.
+ *           candidates of `plan` from the reduced sums (f(w) is taken from fk_acc, so both sides of the
+ *           comparison come from the same kernel); writes theta_out[g] (already halved, admm.py:338) and
+ *           done[g]; leaves the gate undecided if a lower bound failed or no candidate exits.
  *  apply  : w <- (0.5 rho T theta w - G)/(beta + 0.5 rho theta T)           (admm.py:340-343)
  * K = D for ADMM_SRC_X, H for ADMM_SRC_H. */
 /* begin: once per `src` before the first admm_weight_grad of the phase (prepares the zstore refresh operands). */
@@ -134,12 +149,12 @@ int admm_weight_begin(const admm_problem* p, int src, void* stream);
 int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scratch,
                      double* g_acc, double* fw_acc, void* stream);
 int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out,
-                            void* stream);
+                            double* est_acc, void* stream);
 int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scratch, const float* grad,
-                      int k0, int ncand, const int32_t* done, double* fk_acc, void* stream);
-int admm_weight_select(const admm_problem* p, int src, const float* grad, const double* fw_acc,
-                       const double* fk_acc, int k0, int ncand, int final_pass, int32_t* done,
-                       float* theta_out, void* stream);
+                      const admm_probe_plan* plan, const int32_t* done, double* fk_acc, void* stream);
+int admm_weight_select(const admm_problem* p, int src, const double* est_acc, const double* fk_acc,
+                       const admm_probe_plan* plan, int final_pass, int32_t* done, float* theta_out,
+                       void* stream);
 int admm_weight_apply(const admm_problem* p, int src, const float* grad, const float* theta,
                       void* stream);
 

@@ -16,5 +16,5 @@ for s in range(12):
     opt.step()
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     tr = opt.theta_trace(); m = opt.metrics()
-    print(s + 1, f"{dt*1e3:8.1f} ms first_cand={opt._first_cand}", {k: (int(np.log2(v)) if v >= 1 else v) for k, v in tr.items()},
+    print(s + 1, f"{dt*1e3:8.1f} ms hint={opt._hint}", {k: (int(np.log2(v)) if v >= 1 else v) for k, v in tr.items()},
           f"obj={m['objective']:.4g} prim={m['primal_residual']:.4g}")

@@ -7,8 +7,10 @@
 
 #if defined(__CUDACC__)
 #define ADMM_HD __host__ __device__ __forceinline__
+#define ADMM_HDM __host__ __device__ __forceinline__
 #else
 #define ADMM_HD static inline
+#define ADMM_HDM inline
 #endif
 
 namespace admm {
@@ -17,14 +19,58 @@ struct Rho { float i, f, g, o, c, h, y; };
 
 ADMM_HD float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }     // admm.py:235-237
 ADMM_HD float tanh_f(float x) { return tanhf(x); }                         // admm.py:231-233
+
+// Math policies of the per-element closed forms.  Accurate = libm-class functions and IEEE division (the CUDA-core
+// path, the host build, everything the knife-edge parity tests look at).  Fast (device only) = two MUFU ops per
+// activation (ex2.approx + rcp.approx with one Newton step; degree-5 odd polynomial for |x| < 0.6 in tanh) and
+// reciprocal-multiply division, <= 2 ulp: used by the tensor-core epilogues, whose instruction count bounds the kernel.
+struct AccurateMath {
+  ADMM_HDM static float sigmoid(float x) { return sigmoid_f(x); }
+  ADMM_HDM static float tanh(float x) { return tanh_f(x); }
+  ADMM_HDM static float div(float a, float b) { return a / b; }
+};
+#if defined(__CUDACC__)
+struct FastMath {
+  __device__ __forceinline__ static float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
+  // 1/d for normal positive or negative d: rcp.approx + one Newton step (~0.5 ulp)
+  __device__ __forceinline__ static float rcp(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(r, fmaf(-d, r, 1.0f), r);
+  }
+  __device__ __forceinline__ static float sigmoid(float x) {
+    return rcp(1.0f + ex2(-1.4426950408889634f * fmaxf(x, -80.0f)));
+  }
+  __device__ __forceinline__ static float tanh(float x) {
+    const float ax = fminf(fabsf(x), 40.0f);
+    const float e = ex2(-2.8853900817779268f * ax);
+    const float big = (1.0f - e) * rcp(1.0f + e);
+    const float t = x * x;
+    float p = 0.0024976127315312624f;
+    p = fmaf(p, t, -0.008506525307893753f);
+    p = fmaf(p, t, 0.02181374467909336f);
+    p = fmaf(p, t, -0.05396425351500511f);
+    p = fmaf(p, t, 0.133333221077919f);
+    p = fmaf(p, t, -0.3333333432674408f);
+    const float small = fmaf(x * t, p, x);
+    return ax < 0.6f ? small : copysignf(big, x);
+  }
+  __device__ __forceinline__ static float div(float a, float b) { return a * rcp(b); }
+};
+#endif
 // admm.py:239-244, expressed through the activation value itself
 ADMM_HD float dsigmoid_from(float s) { return s * (1.0f - s); }
 ADMM_HD float dtanh_from(float t) { return 1.0f - t * t; }
 
 // admm.py:384-386: -(lam - rho1*act(z) + (rho2*(p2*p3 - var2) - lam2)*p1) / (rho1 + rho2*p1*p1)
+template <class M = AccurateMath>
 ADMM_HD float gate_prox(float lam, float rho1, float act_z, float rho2, float p2p3, float var2,
                         float lam2, float p1) {
-  return -(lam - rho1 * act_z + (rho2 * (p2p3 - var2) - lam2) * p1) / (rho1 + rho2 * p1 * p1);
+  return M::div(-(lam - rho1 * act_z + (rho2 * (p2p3 - var2) - lam2) * p1), rho1 + rho2 * p1 * p1);
 }
 
 struct SweepPoint {
@@ -43,27 +89,28 @@ struct SweepResult {
 // One (sample, hidden unit) of admm.py:345-351 followed by admm.py:504-510 at timestep t.
 // last == true (t == T): h and lambda_h are NOT touched here (admm_last_* does them); the old h and
 // lambda_h still enter the o and c updates exactly as in the reference.
+template <class M = AccurateMath>
 ADMM_HD SweepResult sweep_point(const SweepPoint& s, const Rho& r, bool last) {
   SweepResult out;
-  const float ai = sigmoid_f(s.zi), af = sigmoid_f(s.zf), ag = tanh_f(s.zg), ao = sigmoid_f(s.zo);
+  const float ai = M::sigmoid(s.zi), af = M::sigmoid(s.zf), ag = M::tanh(s.zg), ao = M::sigmoid(s.zo);
   // i: p1 = g_t, p2 = f_t, p3 = c_{t-1}   (admm.py:361-364)
-  out.i = gate_prox(s.li, r.i, ai, r.c, s.f * s.c_prev, s.c, s.lc, s.g);
+  out.i = gate_prox<M>(s.li, r.i, ai, r.c, s.f * s.c_prev, s.c, s.lc, s.g);
   // f: p1 = c_{t-1}, p2 = g_t, p3 = i_t(new)   (admm.py:365-368)
-  out.f = gate_prox(s.lf, r.f, af, r.c, s.g * out.i, s.c, s.lc, s.c_prev);
+  out.f = gate_prox<M>(s.lf, r.f, af, r.c, s.g * out.i, s.c, s.lc, s.c_prev);
   // g: p1 = i_t(new), p2 = f_t(new), p3 = c_{t-1}   (admm.py:369-372)
-  out.g = gate_prox(s.lg, r.g, ag, r.c, out.f * s.c_prev, s.c, s.lc, out.i);
+  out.g = gate_prox<M>(s.lg, r.g, ag, r.c, out.f * s.c_prev, s.c, s.lc, out.i);
   // o: p1 = tanh(c_t old), p2 = p3 = 0, var2 = h_t old   (admm.py:373-379)
-  const float tc_old = tanh_f(s.c);
-  out.o = gate_prox(s.lo, r.o, ao, r.h, 0.0f, s.h, s.lh, tc_old);
+  const float tc_old = M::tanh(s.c);
+  out.o = gate_prox<M>(s.lo, r.o, ao, r.h, 0.0f, s.h, s.lh, tc_old);
   // c: admm.py:388-436 with theta = 0.5 (the loop at :430 never iterates)
-  const float zed = s.h + s.lh / r.h;
+  const float zed = s.h + M::div(s.lh, r.h);
   const float u = tc_old * out.o - zed;
   const float grad = (u * out.o) * (1.0f - tc_old * tc_old);
-  const float A = s.lc / r.c - out.f * s.c_prev - out.i * out.g;
-  out.c = (0.5f * s.c - grad - r.c * A) / (r.c + 0.5f);
+  const float A = M::div(s.lc, r.c) - out.f * s.c_prev - out.i * out.g;
+  out.c = M::div(0.5f * s.c - grad - r.c * A, r.c + 0.5f);
   // h, t < T: admm.py:455-457
-  const float tc_new = tanh_f(out.c);
-  out.h = last ? s.h : (r.h * out.o * tc_new - s.lh) / r.h;
+  const float tc_new = M::tanh(out.c);
+  out.h = last ? s.h : M::div(r.h * out.o * tc_new - s.lh, r.h);
   // duals: admm.py:512-530 (same z as the primal update: weights and h_{t-1} are unchanged)
   const float ri = out.i - ai, rf = out.f - af, rg = out.g - ag, ro = out.o - ao;
   const float rc = out.c - (out.f * s.c_prev + out.i * out.g);
@@ -85,22 +132,24 @@ ADMM_HD SweepResult sweep_point(const SweepPoint& s, const Rho& r, bool last) {
 
 // blocks/lstm.py:80-85
 struct ForwardResult { float i, f, g, o, c, h; };
+template <class M = AccurateMath>
 ADMM_HD ForwardResult forward_point(float zi, float zf, float zg, float zo, float c_prev) {
   ForwardResult out;
-  out.i = sigmoid_f(zi);
-  out.f = sigmoid_f(zf);
-  out.g = tanh_f(zg);
-  out.o = sigmoid_f(zo);
+  out.i = M::sigmoid(zi);
+  out.f = M::sigmoid(zf);
+  out.g = M::tanh(zg);
+  out.o = M::sigmoid(zo);
   out.c = out.f * c_prev + out.i * out.g;
-  out.h = out.o * tanh_f(out.c);
+  out.h = out.o * M::tanh(out.c);
   return out;
 }
 
 // admm.py:302-312: residual u = act(z) - lambda/rho - gate; R = u * act'(z).  gate_is_g selects tanh.
+template <class M = AccurateMath>
 ADMM_HD float grad_point(float z, float lam, float gate, float rho, bool gate_is_g, float* u_out) {
-  const float a = gate_is_g ? tanh_f(z) : sigmoid_f(z);
+  const float a = gate_is_g ? M::tanh(z) : M::sigmoid(z);
   const float d = gate_is_g ? dtanh_from(a) : dsigmoid_from(a);
-  const float u = a - lam / rho - gate;
+  const float u = a - M::div(lam, rho) - gate;
   *u_out = u;
   return u * d;
 }

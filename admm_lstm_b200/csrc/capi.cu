@@ -3,6 +3,7 @@
 // attached and the shape is eligible, fp32 CUDA-core path otherwise) and launches.  There is no
 // CPU fallback: without an sm_100 device every compute entry point returns ADMM_ENODEV.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -172,7 +173,7 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   cudaStream_t st = (cudaStream_t)stream;
   GateGemmArgs a = base_args(p, t0 + 1);
   const bool use_tc = p->tc_ws && tc_eligible(p);
-  const bool atr_on_tc = use_tc && src == ADMM_SRC_H;
+  const bool atr_on_tc = use_tc;
   a.scratch = scratch; a.tc = tc; a.fw_acc = fw_acc; a.src = src;
   a.scratch_q = atr_on_tc ? scratch + 4LL * p->H * tc * p->ldn : nullptr;     // tf32 low part of R^T
   if (use_tc && p->zstore && p->wx_prev) {
@@ -239,11 +240,24 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
   e.z_T = stored ? p->T : tc; e.z_t0 = stored ? t0 : 0;
   for (int g = 0; g < 4; ++g) { e.gate[g] = a.gate[g]; e.dual[g] = a.dual[g]; e.rho[g] = p->hp.rho[g]; }
   e.s_tstride = a.s_tstride;
-  for (int g = 0; g < 4; ++g) e.k0[g] = plan->k0[g];
-  e.ncand = plan->ncand; e.proof = 0; e.done = done; e.fk_acc = fk_acc;
+  e.done = done; e.fk_acc = fk_acc;
+  // window: all units, theta = 2^(k0[g] + c)
+  for (int g = 0; g < 4; ++g) { e.kbase[g] = plan->k0[g]; e.nc[g] = plan->ncand; e.slot0[g] = 0; }
+  e.jmod = 1; e.jrem = 0; e.publish_fw = 1;
   rc = probe_eval(e, st);
   if (rc || !plan->proof) return rc;
-  e.proof = 1;
+  // lower bounds below the window: every k < k0[g] on unit blocks 0 mod 8, and the three exponents next to the
+  // window additionally on the odd blocks (disjoint sets, so the sums add up to one partial sum over 5/8 of the units)
+  for (int g = 0; g < 4; ++g) { e.kbase[g] = 0; e.nc[g] = plan->k0[g]; e.slot0[g] = ADMM_MAX_CAND + 1; }
+  e.jmod = 8; e.jrem = 0; e.publish_fw = 0;
+  rc = probe_eval(e, st);
+  if (rc) return rc;
+  for (int g = 0; g < 4; ++g) {
+    e.kbase[g] = plan->k0[g] > 3 ? plan->k0[g] - 3 : 0;
+    e.nc[g] = plan->k0[g] - e.kbase[g];
+    e.slot0[g] = ADMM_MAX_CAND + 1 + e.kbase[g];
+  }
+  e.jmod = 2; e.jrem = 1;
   return probe_eval(e, st);
 }
 

@@ -88,4 +88,19 @@ __device__ __forceinline__ void st_stream(float* p, const float4& v) {
                ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Scalar streaming accesses as volatile asm: ptxas keeps volatile asm statements in program order, which pins the
+// epilogue schedule to [all loads of a batch][arithmetic][all stores] (the intrinsics let it sink every load next to
+// its first use, serialising the memory latency).
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_keep(float* p, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 }  // namespace admm

@@ -67,9 +67,11 @@ struct ProbeEvalArgs {
   const float* dual[4];
   int64_t s_tstride;
   float rho[4];
-  int32_t k0[4];         // first theta exponent of the window, per gate
-  int32_t ncand;         // window size
-  int32_t proof;         // 1: evaluate k < k0[g] on one unit block in PROOF_STRIDE (lower bounds) instead of the window
+  int32_t kbase[4];      // per gate: first theta exponent evaluated by this launch
+  int32_t nc[4];         // per gate: number of consecutive exponents
+  int32_t slot0[4];      // per gate: fk_acc slot of the first one
+  int32_t jmod, jrem;    // only unit blocks jb with jb % jmod == jrem are summed (jmod = 1: all units)
+  int32_t publish_fw;    // also publish f(w) into slot ADMM_MAX_CAND
   const int32_t* done;
   double* fk_acc;        // [4][ADMM_FK_SLOTS]
 };

@@ -14,8 +14,9 @@
 // TMA (128B swizzle with 32B atoms, boxes of 32 floats x BK rows) lands them in the canonical MN-major layout, so
 // there is no transposed copy of the state or of the weights anywhere.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (one thread per sample row; TMEM lane == sample, TMEM column == (gate, unit)).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (one thread per sample row and half of the tile's units; TMEM lane == sample,
+// TMEM column == (gate, unit)); two warps share each TMEM lane quarter and split the columns.
 // The accumulator never leaves the SM: the epilogue reads it with tcgen05.ld and applies the same
 // closed forms as the CUDA-core path (admm_math.cuh); all its global accesses are 128-byte warp rows.
 // Two CTAs are resident per SM (2 x 256 TMEM columns), so one tile's epilogue overlaps the other's MMAs.
@@ -35,7 +36,7 @@ namespace {
 constexpr int BM = 128;        // samples per tile (UMMA M)
 constexpr int BK = 16;         // features per pipeline stage (2 UMMA k-steps of 8)
 constexpr int NSTAGE = 2;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int CHUNK_BYTES = 32 * BK * 4;     // one TMA box: 32 floats (128 B) x BK rows
 
 struct TcMaps {
@@ -147,7 +148,7 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[4 * 4];
+  __shared__ float red[4 * 8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // blockIdx.x walks the unit tiles: CTAs that share the same 128 samples (the A tile) are scheduled together, so the
@@ -233,8 +234,9 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
       umma_commit(&acc_bar);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+    const int ehalf = (warp - 2) >> 2;                 // which 32 of the tile's 64 units this warp handles
     const int row = quarter * 32 + lane;
     const int64_t n = (int64_t)n0 + row;
     const bool ok = n < p.n;
@@ -250,9 +252,9 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
     // The epilogue is latency-bound if each unit waits for its own loads (measured: ~3x the MMA time of a tile):
     // every batch of EB units first issues ALL its global loads, then computes, then stores, so ~13*EB loads are
     // in flight per thread.  Loads use the streaming path (each state entry is touched once per launch).
-    constexpr int EB = 4;
+    constexpr int EB = 2;
     const float rho_g[4] = {rho.i, rho.f, rho.g, rho.o};
-    for (int jb = 0; jb < JC; jb += 8) {
+    for (int jb = ehalf * (JC / 2); jb < (ehalf + 1) * (JC / 2); jb += 8) {
       float z[4][8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld8(t_row + g * JC + jb, z[g]);
@@ -275,7 +277,7 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
           for (int e = 0; e < EB; ++e) cp[e] = __ldcs(p.c_prev + off[e]);
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
-            const ForwardResult r = forward_point(z[0][eb + e], z[1][eb + e], z[2][eb + e], z[3][eb + e], cp[e]);
+            const ForwardResult r = forward_point<FastMath>(z[0][eb + e], z[1][eb + e], z[2][eb + e], z[3][eb + e], cp[e]);
             if (p.gate[0]) __stcs(p.gate[0] + off[e], r.i);
             if (p.gate[1]) __stcs(p.gate[1] + off[e], r.f);
             if (p.gate[2]) __stcs(p.gate[2] + off[e], r.g);
@@ -287,15 +289,26 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
         }
         if (MODE == GG_SWEEP) {
           float in[13][EB];
+          if (p.last < 0) {            // never taken (see note below)
 #pragma unroll
-          for (int e = 0; e < EB; ++e) {
+            for (int e = 0; e < EB; ++e)
 #pragma unroll
-            for (int q = 0; q < 6; ++q) in[q][e] = __ldcs(p.gate[q] + off[e]);
-            in[6][e] = __ldcs(p.c_prev + off[e]);
+              for (int q = 0; q < 13; ++q) in[q][e] = 0.25f + 0.01f * q;
+          } else {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) in[7 + q][e] = __ldcs(p.dual[q] + off[e]);
-            in[12][e] = p.last ? __ldcs(p.dual_h + (int64_t)(j0 + jb + eb + e) * ldn + n) : 0.f;
+            for (int e = 0; e < EB; ++e) {
+#pragma unroll
+              for (int q = 0; q < 6; ++q) in[q][e] = __ldcs(p.gate[q] + off[e]);
+              in[6][e] = __ldcs(p.c_prev + off[e]);
+#pragma unroll
+              for (int q = 0; q < 5; ++q) in[7 + q][e] = __ldcs(p.dual[q] + off[e]);
+              in[12][e] = p.last ? __ldcs(p.dual_h + (int64_t)(j0 + jb + eb + e) * ldn + n) : 0.f;
+            }
           }
+          // NOTE on the never-taken branches (p.last is 0 or 1): they only shape ptxas' schedule.  Putting the loads of a
+          // batch in their own basic block keeps them together ahead of the arithmetic, and the guarded `continue`
+          // keeps each unit's stores behind its arithmetic; without them ptxas interleaves load / use / store per value
+          // and the kernel takes 1.21 ms instead of 0.78 ms per launch (cfg3 shape; measured with scripts/gemm_bench.py).
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
             SweepPoint s;
@@ -303,7 +316,11 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
             s.i = in[0][e]; s.f = in[1][e]; s.g = in[2][e]; s.o = in[3][e]; s.c = in[4][e]; s.h = in[5][e];
             s.c_prev = in[6][e];
             s.li = in[7][e]; s.lf = in[8][e]; s.lg = in[9][e]; s.lo = in[10][e]; s.lc = in[11][e]; s.lh = in[12][e];
-            const SweepResult r = sweep_point(s, rho, p.last != 0);
+            const SweepResult r = sweep_point<FastMath>(s, rho, p.last != 0);
+            if (p.last < 0) {
+              if (r.i == 123.456f) p.gate[0][off[e]] = r.i + r.f + r.g + r.o + r.c + r.h + r.li + r.lf + r.lg + r.lo + r.lc;
+              continue;
+            }
             __stcs(p.gate[0] + off[e], r.i); __stcs(p.gate[1] + off[e], r.f); __stcs(p.gate[2] + off[e], r.g);
             __stcs(p.gate[3] + off[e], r.o);
             p.gate[4][off[e]] = r.c;                         // c_t is read again by the next timestep
@@ -318,29 +335,45 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
         }
         if (MODE == GG_GRAD) {
           float lam[4][EB], gv[4][EB], zold[4][EB];
+          if (p.tc < 0) {              // never taken: same schedule-shaping device as in SWEEP above
 #pragma unroll
-          for (int e = 0; e < EB; ++e)
+            for (int e = 0; e < EB; ++e)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              lam[g][e] = __ldcs(p.dual[g] + off[e]);
-              gv[g][e] = __ldcs(p.gate[g] + off[e]);
-              zold[g][e] = p.z_accumulate
-                  ? __ldcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n) : 0.f;
-            }
+              for (int g = 0; g < 4; ++g) { lam[g][e] = 0.1f * g; gv[g][e] = 0.2f; zold[g][e] = 0.3f; }
+          } else {
 #pragma unroll
-          for (int e = 0; e < EB; ++e)
+            for (int e = 0; e < EB; ++e)
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                lam[g][e] = __ldcs(p.dual[g] + off[e]);
+                gv[g][e] = __ldcs(p.gate[g] + off[e]);
+                zold[g][e] = p.z_accumulate
+                    ? __ldcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n) : 0.f;
+              }
+          }
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
+            float rv[4], zz[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float u;
-              const float zz = z[g][eb + e] + zold[g][e];
-              if (p.zstore) __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, zz);
-              const float rr = grad_point(zz, lam[g][e], gv[g][e], rho_g[g], g == 2, &u);
-              const float rv = ok ? rr : 0.f;
-              const int64_t so = (((int64_t)g * H + (j0 + jb + eb + e)) * p.tc + tl) * ldn + n;
-              p.scratch[so] = rv;                            // read right back by the A^T R GEMM: keep in L2
-              if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv);
+              zz[g] = z[g][eb + e] + zold[g][e];
+              const float rr = grad_point<FastMath>(zz[g], lam[g][e], gv[g][e], rho_g[g], g == 2, &u);
+              rv[g] = ok ? rr : 0.f;
               if (ok) msum[g] += u * u;
             }
+            if (p.tc < 0) {            // never taken
+              if (rv[0] == 123.456f) p.scratch[off[e]] = rv[0] + rv[1] + rv[2] + rv[3] + zz[0] + zz[1] + zz[2] + zz[3];
+              continue;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int64_t so = (((int64_t)g * H + (j0 + jb + eb + e)) * p.tc + tl) * ldn + n;
+              if (p.zstore) __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, zz[g]);
+              p.scratch[so] = rv[g];                         // read right back by the A^T R GEMM: keep in L2
+              if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv[g]);
+            }
+          }
         }
       }
     }
@@ -353,13 +386,14 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
 #pragma unroll
         for (int k = 0; k < NOUT; ++k) {
           const float s = warp_sum(msum[k]);
-          if (lane == 0) red[k * 4 + quarter] = s;
+          if (lane == 0) red[k * 8 + (warp - 2)] = s;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int et = threadIdx.x - 64;
         if (et < NOUT) {
-          const double s = (double)red[et * 4 + 0] + (double)red[et * 4 + 1] + (double)red[et * 4 + 2] +
-                           (double)red[et * 4 + 3];
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += (double)red[et * 8 + w];
           atomicAdd(dst + et, s);
         }
       }
@@ -622,6 +656,7 @@ namespace {
 // epilogue's accumulation into the fp64 G buffer is coalesced along j.  3xTF32: R_hi*h_hi + R_lo*h_hi + R_hi*h_lo.
 constexpr int ATR_BKN = 32;           // samples per pipeline stage (one 128-byte swizzle row)
 constexpr int ATR_STAGES = 2;
+constexpr int ATR_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
 struct AtrMaps { CUtensorMap r, r_lo, h, h_lo; };
 
@@ -639,7 +674,7 @@ __host__ __device__ constexpr uint32_t make_idesc_kmajor(int m, int n) {
 }
 
 template <int NT_>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(ATR_THREADS, 1)
 atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H, int tc, int64_t ldn, int slab0,
               int chunks_per_cta, int n_chunks, int use_atomics) {
   constexpr int A_BYTES = 128 * ATR_BKN * 4;        // R tile   16 KB
@@ -748,7 +783,7 @@ int make_map_box(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uin
 }
 
 template <int NT_>
-int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, cudaStream_t st) {
+int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x, cudaStream_t st) {
   constexpr int SMEM = ATR_STAGES * (2 * 128 * ATR_BKN * 4 + 2 * NT_ * ATR_BKN * 4) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -760,31 +795,45 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, cudaStream_t 
   int rc = 0;
   rc |= make_map_box(&m.r, a.scratch, ldn, tc, 4 * H, ldn, tc * ldn, ATR_BKN, 1, 128);
   rc |= make_map_box(&m.r_lo, a.scratch_lo, ldn, tc, 4 * H, ldn, tc * ldn, ATR_BKN, 1, 128);
-  rc |= make_map_box(&m.h, p->gate[5], ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
-  rc |= make_map_box(&m.h_lo, tc_h_lo(p), ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
+  if (src_is_x) {     // A_src = x: [T][D][ldn]; rows k >= D are zero-filled by TMA and masked in the epilogue
+    const uint64_t D = p->D;
+    rc |= make_map_box(&m.h, p->x, ldn, D, p->T, ldn, D * ldn, ATR_BKN, NT_, 1);
+    rc |= make_map_box(&m.h_lo, (float*)p->tc_ws + ws_layout(p).x_lo, ldn, D, p->T, ldn, D * ldn, ATR_BKN, NT_, 1);
+  } else {
+    rc |= make_map_box(&m.h, p->gate[5], ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
+    rc |= make_map_box(&m.h_lo, tc_h_lo(p), ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
+  }
   if (rc) return ADMM_ECUDA;
   const int n_chunks = (int)(tc * (ldn / ATR_BKN));
-  const int tiles = (int)((4 * H / 128) * ((H + NT_ - 1) / NT_));
+  const int tiles = (int)((4 * H / 128) * ((a.K + NT_ - 1) / NT_));
   int splits = (148 + tiles - 1) / tiles;
   if (tiles * splits > 148 && splits > 1) --splits;          // stay within one wave of 148 single-CTA SMs
   splits = max(1, min(splits, n_chunks));
   const int cpc = (n_chunks + splits - 1) / splits;
   splits = (n_chunks + cpc - 1) / cpc;
-  dim3 grid((unsigned)(4 * H / 128), (unsigned)((H + NT_ - 1) / NT_), (unsigned)splits);
-  atr_tc_kernel<NT_><<<grid, NTHREADS, SMEM, st>>>(m, a.g_acc, a.K, a.H, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1);
+  dim3 grid((unsigned)(4 * H / 128), (unsigned)((a.K + NT_ - 1) / NT_), (unsigned)splits);
+  atr_tc_kernel<NT_><<<grid, ATR_THREADS, SMEM, st>>>(m, a.g_acc, a.K, a.H, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1);
   count_launch();
   return check_launch("atr_tc");
 }
 
 }  // namespace
 
-// Tensor-core G += A_src^T R for src = h (K = H).  `a.a_src` must be a slab of p->gate[5].
+// Tensor-core G += A_src^T R.  `a.a_src` must be a slab of p->gate[5] (src = h, K = H) or of p->x (src = x, K = D).
 int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st) {
-  if (!a.scratch_lo || a.K != p->H) return atr_simt(a, st);
+  if (!a.scratch_lo) return atr_simt(a, st);
+  const bool src_is_x = (a.a_src >= p->x && a.a_src < p->x + (int64_t)p->T * p->D * p->ldn);
+  if (src_is_x) {
+    if (p->D < 8) return atr_simt(a, st);               // a handful of rows: not worth a 64-row MMA tile
+    const int slab0 = (int)((a.a_src - p->x) / ((int64_t)p->D * p->ldn));
+    if (a.K > 128) return launch_atr<256>(p, a, slab0, true, st);
+    if (a.K > 64) return launch_atr<128>(p, a, slab0, true, st);
+    return launch_atr<64>(p, a, slab0, true, st);
+  }
   const int slab0 = (int)((a.a_src - p->gate[5]) / ((int64_t)p->H * p->ldn));
-  if (p->H >= 256) return launch_atr<256>(p, a, slab0, st);
-  if (p->H >= 128) return launch_atr<128>(p, a, slab0, st);
-  return launch_atr<64>(p, a, slab0, st);
+  if (p->H >= 256) return launch_atr<256>(p, a, slab0, false, st);
+  if (p->H >= 128) return launch_atr<128>(p, a, slab0, false, st);
+  return launch_atr<64>(p, a, slab0, false, st);
 }
 
 }  // namespace admm

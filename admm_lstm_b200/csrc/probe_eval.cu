@@ -23,37 +23,6 @@ namespace {
 constexpr int NT = 256;
 constexpr int JB = 8;          // hidden units per block
 constexpr int NCS = ADMM_FK_SLOTS;
-constexpr int PROOF_STRIDE = 8;   // lower-bound sums use one block of JB units in PROOF_STRIDE
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 1/d for d in [1, inf): rcp.approx + one Newton step (~0.5 ulp)
-__device__ __forceinline__ float rcp_polished(float d) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  return fmaf(r, fmaf(-d, r, 1.0f), r);
-}
-__device__ __forceinline__ float sigmoid_2mufu(float x) {
-  const float e = ex2_approx(-1.4426950408889634f * fmaxf(x, -80.0f));
-  return rcp_polished(1.0f + e);
-}
-__device__ __forceinline__ float tanh_2mufu(float x) {
-  const float ax = fminf(fabsf(x), 40.0f);
-  const float e = ex2_approx(-2.8853900817779268f * ax);
-  const float big = (1.0f - e) * rcp_polished(1.0f + e);
-  const float t = x * x;
-  float p = 0.0024976127315312624f;
-  p = fmaf(p, t, -0.008506525307893753f);
-  p = fmaf(p, t, 0.02181374467909336f);
-  p = fmaf(p, t, -0.05396425351500511f);
-  p = fmaf(p, t, 0.133333221077919f);
-  p = fmaf(p, t, -0.3333333432674408f);
-  const float small = fmaf(x * t, p, x);
-  return ax < 0.6f ? small : copysignf(big, x);
-}
 
 template <int NC, bool IS_G>
 __device__ __forceinline__ void accumulate(const float4& z4, const float4& q4, const float4& lam4, const float4& gv4,
@@ -68,7 +37,7 @@ __device__ __forceinline__ void accumulate(const float4& z4, const float4& q4, c
 #pragma unroll
     for (int k = 0; k <= NC; ++k) {
       const float zz = (k < NC) ? fmaf(q[e], inv_theta[k], z[e]) : z[e];
-      const float a = IS_G ? tanh_2mufu(zz) : sigmoid_2mufu(zz);
+      const float a = IS_G ? FastMath::tanh(zz) : FastMath::sigmoid(zz);
       const float u = (a - lr) - gv[e];
       acc[k] = fmaf(u, u, acc[k]);
     }
@@ -83,17 +52,14 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
   __shared__ float red[(NC + 1) * (NT / 32)];
   if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int jstep = p.proof ? PROOF_STRIDE : 1;
 
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int nb = (int)(item % n_nb);
-    const int jb = (int)((item / n_nb) % n_jb) * jstep;
+    const int jb = (int)((item / n_nb) % n_jb) * p.jmod + p.jrem;
     const int gt = (int)(item / ((int64_t)n_nb * n_jb));
     const int g = gt & 3, tl = gt >> 2;
     if (p.done[g]) continue;
-    // window: theta = 2^(k0[g]+k), k < ncand ; proof: theta = 2^k, k < k0[g]
-    const int kbase = p.proof ? 0 : p.k0[g];
-    const int nc = p.proof ? p.k0[g] : p.ncand;
+    const int kbase = p.kbase[g], nc = p.nc[g];
     if (nc <= 0) continue;
     float inv_theta[NC];
 #pragma unroll
@@ -129,10 +95,10 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
     __syncthreads();
     if (threadIdx.x <= NC) {
       const int k = threadIdx.x;
-      if (k < nc || (k == NC && !p.proof)) {
+      if (k < nc || (k == NC && p.publish_fw)) {
         double s = 0.0;
         for (int w = 0; w < NT / 32; ++w) s += (double)red[k * (NT / 32) + w];
-        const int slot = (k == NC) ? ADMM_MAX_CAND : (p.proof ? ADMM_MAX_CAND + 1 + k : k);
+        const int slot = (k == NC) ? ADMM_MAX_CAND : p.slot0[g] + k;
         atomicAdd(p.fk_acc + g * NCS + slot, s);
       }
     }
@@ -144,13 +110,10 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
 
 int probe_eval(const ProbeEvalArgs& a, cudaStream_t st) {
   const int n_nb = (int)((a.ldn / 4 + NT - 1) / NT);
-  int n_jb = (a.H + JB - 1) / JB;
-  int nc = a.ncand;
-  if (a.proof) {
-    n_jb = (n_jb + PROOF_STRIDE - 1) / PROOF_STRIDE;
-    nc = max(max(a.k0[0], a.k0[1]), max(a.k0[2], a.k0[3]));
-    if (nc <= 0) return ADMM_OK;
-  }
+  const int n_jb_all = (a.H + JB - 1) / JB;
+  const int n_jb = (n_jb_all - a.jrem + a.jmod - 1) / a.jmod;
+  const int nc = max(max(a.nc[0], a.nc[1]), max(a.nc[2], a.nc[3]));
+  if (nc <= 0 || n_jb <= 0) return ADMM_OK;
   const int64_t n_items = (int64_t)n_nb * n_jb * 4 * a.tc;
   const unsigned grid = (unsigned)(n_items < 148 * 8 ? n_items : 148 * 8);
   if (nc <= 8) probe_eval_kernel<8><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);

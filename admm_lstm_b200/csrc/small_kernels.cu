@@ -338,7 +338,10 @@ __global__ void weight_select_kernel(const double* est_acc, const double* fk_acc
   if (plan.proof) {
     for (int k = 0; k < k0; ++k) {
       const float lower = 0.5f * rho * (float)fk[ADMM_MAX_CAND + 1 + k];
-      if (!(lower > est(k))) return;                 // not provable from the subsample: a full pass will decide
+      if (!(lower > est(k))) {                       // not provable from the subsample: a full pass will decide
+        done[4 + g] = 1; done[8 + g] = k;
+        return;
+      }
     }
   }
   int found = -1;
@@ -351,6 +354,8 @@ __global__ void weight_select_kernel(const double* est_acc, const double* fk_acc
   if (found >= 0) {
     theta_out[g] = ldexpf(1.0f, found - 1);            // theta /= 2 (admm.py:338)
     done[g] = 1;
+  } else if (!final_pass) {
+    done[4 + g] = 2; done[8 + g] = k0 + plan.ncand;    // diagnostics: window exhausted
   } else if (final_pass) {
     theta_out[g] = ldexpf(1.0f, k0 + plan.ncand - 1);  // iteration cap (the reference has none)
     done[g] = 1;

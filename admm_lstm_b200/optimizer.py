@@ -165,7 +165,7 @@ class ADMMBasedOptimizer(object):
         self._acc_last = torch.zeros(1 + 3 * 4, dtype=torch.float64, device=dev)
         self._metrics = torch.zeros(_lib.ADMM_N_METRICS, dtype=torch.float64, device=dev)
         self._grad = torch.zeros(4 * kmax * H, dtype=f32, device=dev)
-        self._done = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._done = torch.zeros(12, dtype=torch.int32, device=dev)      # [0,4) decided, [4,12) diagnostics
         self._theta_w = torch.zeros(8, dtype=f32, device=dev)       # [src][gate]
         self._theta_h = torch.zeros(1, dtype=f32, device=dev)
         # ring of pinned read-backs of the chosen thetas: the host runs ahead of the device (it is throttled only

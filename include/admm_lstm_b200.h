@@ -57,7 +57,8 @@ typedef struct admm_hyper {
 
 /* Which thetas a probe pass evaluates, per gate (identical on every rank: derived from replicated data).
  * Window: theta = 2^(k0[g]+c), c < ncand, summed over ALL units -> fk_acc[g][c]; f(w) -> fk_acc[g][32].
- * proof != 0: additionally, for k < k0[g], the same sum over one unit block in eight -> fk_acc[g][33+k].  A
+ * proof != 0: additionally, for k < k0[g], the same sum over a fixed subset of the units (1/8 of them, 5/8 for the
+ * three exponents next to the window) -> fk_acc[g][33+k].  A
  * partial sum of squares is a rigorous LOWER bound of f(w + G/2^k); if even the bound exceeds est_k the
  * reference's loop provably continues past k (admm.py:334) without the full evaluation.  If a bound does
  * not prove it, the pass stays undecided for that gate and a full pass from k = 0 follows. */
@@ -141,7 +142,9 @@ int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream);
  *  select : per gate, replays `while f(beta) > est(beta, theta): theta *= 2` (admm.py:331-338) over the
  *           candidates of `plan` from the reduced sums (f(w) is taken from fk_acc, so both sides of the
  *           comparison come from the same kernel); writes theta_out[g] (already halved, admm.py:338) and
- *           done[g]; leaves the gate undecided if a lower bound failed or no candidate exits.
+ *           done[g]; leaves the gate undecided if a lower bound failed or no candidate exits.  `done` has 12
+ *           entries: [0,4) decided flags, [4,8) diagnostics of the last undecided pass (1 = bound not conclusive,
+ *           2 = window exhausted), [8,12) the exponent concerned.
  *  apply  : w <- (0.5 rho T theta w - G)/(beta + 0.5 rho theta T)           (admm.py:340-343)
  * K = D for ADMM_SRC_X, H for ADMM_SRC_H. */
 /* begin: once per `src` before the first admm_weight_grad of the phase (prepares the zstore refresh operands). */

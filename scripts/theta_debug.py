@@ -15,6 +15,6 @@ for s in range(12):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     opt.step()
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    tr = opt.theta_trace(); m = opt.metrics()
+    tr = opt.theta_trace(); m = opt.metrics(); dn = opt._done.cpu().tolist()
     print(s + 1, f"{dt*1e3:8.1f} ms hint={opt._hint}", {k: (int(np.log2(v)) if v >= 1 else v) for k, v in tr.items()},
-          f"obj={m['objective']:.4g} prim={m['primal_residual']:.4g}")
+          f"obj={m['objective']:.4g} prim={m['primal_residual']:.4g} diag(h-phase)={dn[4:]}")

@@ -21,6 +21,7 @@
 // closed forms as the CUDA-core path (admm_math.cuh); all its global accesses are 128-byte warp rows.
 // Two CTAs are resident per SM (2 x 256 TMEM columns), so one tile's epilogue overlaps the other's MMAs.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -69,6 +70,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
@@ -139,122 +145,23 @@ struct TcRange {
   int b_is_grad;      // 0: B = (wx | wh) hi/lo ; 1: B = gradient hi/lo, k relative to kb_begin
 };
 
+// Epilogue of one tile for the units [u_begin, u_end) (multiples of 8) of the calling warp's 32 sample rows: reads the
+// accumulator columns from TMEM (t_row = TMEM address of the warp's lane quarter, accumulator buffer included) and
+// applies the closed forms of admm_math.cuh with coalesced (lane == sample) global accesses.
 template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, 2)
-gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0, const TcRange rng) {
-  using C = Cfg;
-  constexpr int JC = C::JC;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float red[4 * 8];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // blockIdx.x walks the unit tiles: CTAs that share the same 128 samples (the A tile) are scheduled together, so the
-  // state is streamed from HBM once per launch and re-used from L2; the weights (a few MB) stay L2-resident anyway.
-  const int j0 = blockIdx.x * JC;
-  const int n0 = blockIdx.y * BM;
-  const int tl = blockIdx.z;
-  const int D = p.D, H = p.H;
-  const int nkx = (D + BK - 1) / BK, nkh = (H + BK - 1) / BK, nkb = nkx + nkh;
-
-  if (MODE == GG_RAWZ && p.done) {
-    if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
-  }
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&acc_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  (void)nkb;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
-        const int li = kb - rng.kb_begin;
-        const int s = li % NSTAGE, it = li / NSTAGE;
-        if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
-        const bool is_x = kb < nkx;
-        const int k0 = (is_x ? kb : kb - nkx) * BK;
-        uint8_t* st = smem + s * C::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES);
-        const CUtensorMap* ma = is_x ? &maps.x : &maps.h;
-        const CUtensorMap* ml = is_x ? &maps.x_lo : &maps.h_lo;
-        const int slab = slab0 + tl;
-#pragma unroll
-        for (int c = 0; c < BM / 32; ++c) {
-          tma_load_3d(st + c * CHUNK_BYTES, ma, &full_bar[s], n0 + 32 * c, k0, slab);
-          tma_load_3d(st + C::A_BYTES + c * CHUNK_BYTES, ml, &full_bar[s], n0 + 32 * c, k0, slab);
-        }
-        const CUtensorMap* bh = rng.b_is_grad ? &maps.gx_hi : (is_x ? &maps.wx_hi : &maps.wh_hi);
-        const CUtensorMap* bl = rng.b_is_grad ? &maps.gx_lo : (is_x ? &maps.wx_lo : &maps.wh_lo);
-        const int kb0 = rng.b_is_grad ? li * BK : k0;
-        uint8_t* sb = st + 2 * C::A_BYTES;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int c = 0; c < JC / 32; ++c) {
-            const int chunk = g * (JC / 32) + c;
-            tma_load_3d(sb + chunk * CHUNK_BYTES, bh, &full_bar[s], j0 + 32 * c, kb0, g);
-            tma_load_3d(sb + C::B_BYTES + chunk * CHUNK_BYTES, bl, &full_bar[s], j0 + 32 * c, kb0, g);
-          }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, C::NCOL);
-      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
-        const int li = kb - rng.kb_begin;
-        const int s = li % NSTAGE, it = li / NSTAGE;
-        mbar_wait(&full_bar[s], it & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + C::A_BYTES;
-        const uint32_t b_hi = st + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint32_t off = ks * 1024;
-          const uint32_t acc0 = (li > 0 || ks > 0) ? 1u : 0u;
-          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc0);
-          umma_tf32(tmem_base, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
-          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
-        }
-        umma_commit(&empty_bar[s]);
-      }
-      umma_commit(&acc_bar);
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
-    const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
-    const int ehalf = (warp - 2) >> 2;                 // which 32 of the tile's 64 units this warp handles
-    const int row = quarter * 32 + lane;
-    const int64_t n = (int64_t)n0 + row;
-    const bool ok = n < p.n;
-    const int64_t ldn = p.ldn;
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const Rho rho = p.rho;
-    const int64_t soff = (int64_t)tl * p.s_tstride;
-    constexpr int NM = 4;
-    float msum[NM] = {0.f, 0.f, 0.f, 0.f};
-
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
+__device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t_row, int u_begin, int u_end, int j0,
+                                               int64_t n, bool ok, int tl, float (&msum)[4]) {
+  constexpr int JC = Cfg::JC;
+  const int H = p.H;
+  const int64_t ldn = p.ldn;
+  const Rho rho = p.rho;
+  const int64_t soff = (int64_t)tl * p.s_tstride;
     // The epilogue is latency-bound if each unit waits for its own loads (measured: ~3x the MMA time of a tile):
     // every batch of EB units first issues ALL its global loads, then computes, then stores, so ~13*EB loads are
     // in flight per thread.  Loads use the streaming path (each state entry is touched once per launch).
     constexpr int EB = 2;
     const float rho_g[4] = {rho.i, rho.f, rho.g, rho.o};
-    for (int jb = ehalf * (JC / 2); jb < (ehalf + 1) * (JC / 2); jb += 8) {
+    for (int jb = u_begin; jb < u_end; jb += 8) {
       float z[4][8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld8(t_row + g * JC + jb, z[g]);
@@ -377,6 +284,112 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
         }
       }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 2)
+gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0, const TcRange rng) {
+  using C = Cfg;
+  constexpr int JC = C::JC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[4 * 8];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.x walks the unit tiles: CTAs that share the same 128 samples (the A tile) are scheduled together, so the
+  // state is streamed from HBM once per launch and re-used from L2; the weights (a few MB) stay L2-resident anyway.
+  const int j0 = blockIdx.x * JC;
+  const int n0 = blockIdx.y * BM;
+  const int tl = blockIdx.z;
+  const int D = p.D, H = p.H;
+  const int nkx = (D + BK - 1) / BK, nkh = (H + BK - 1) / BK, nkb = nkx + nkh;
+
+  if (MODE == GG_RAWZ && p.done) {
+    if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  (void)nkb;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
+        const int li = kb - rng.kb_begin;
+        const int s = li % NSTAGE, it = li / NSTAGE;
+        if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
+        const bool is_x = kb < nkx;
+        const int k0 = (is_x ? kb : kb - nkx) * BK;
+        uint8_t* st = smem + s * C::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES);
+        const CUtensorMap* ma = is_x ? &maps.x : &maps.h;
+        const CUtensorMap* ml = is_x ? &maps.x_lo : &maps.h_lo;
+        const int slab = slab0 + tl;
+        // one 4-D box per operand tile: dims (32 samples, features, 32-sample chunk, slab) land as [chunk][k][32]
+        tma_load_4d(st, ma, &full_bar[s], 0, k0, n0 / 32, slab);
+        tma_load_4d(st + C::A_BYTES, ml, &full_bar[s], 0, k0, n0 / 32, slab);
+        const CUtensorMap* bh = rng.b_is_grad ? &maps.gx_hi : (is_x ? &maps.wx_hi : &maps.wh_hi);
+        const CUtensorMap* bl = rng.b_is_grad ? &maps.gx_lo : (is_x ? &maps.wx_lo : &maps.wh_lo);
+        const int kb0 = rng.b_is_grad ? li * BK : k0;
+        uint8_t* sb = st + 2 * C::A_BYTES;
+        // dims (32 units, features, 32-unit chunk, gate): lands as [gate][chunk][k][32] = the (gate, unit) column order
+        tma_load_4d(sb, bh, &full_bar[s], 0, kb0, j0 / 32, 0);
+        tma_load_4d(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 32, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, C::NCOL);
+      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
+        const int li = kb - rng.kb_begin;
+        const int s = li % NSTAGE, it = li / NSTAGE;
+        mbar_wait(&full_bar[s], it & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + C::A_BYTES;
+        const uint32_t b_hi = st + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t off = ks * 1024;
+          const uint32_t acc0 = (li > 0 || ks > 0) ? 1u : 0u;
+          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc0);
+          umma_tf32(tmem_base, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
+          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+    const int ehalf = (warp - 2) >> 2;                 // which 32 of the tile's 64 units this warp handles
+    const int row = quarter * 32 + lane;
+    const int64_t n = (int64_t)n0 + row;
+    const bool ok = n < p.n;
+    const int64_t ldn = p.ldn;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const Rho rho = p.rho;
+    const int64_t soff = (int64_t)tl * p.s_tstride;
+    constexpr int NM = 4;
+    float msum[NM] = {0.f, 0.f, 0.f, 0.f};
+
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    epilogue_units<MODE>(p, t_row, ehalf * (JC / 2), (ehalf + 1) * (JC / 2), j0, n, ok, tl, msum);
     tc_fence_before();
     // block-level reduction of the metric partials over the 4 epilogue warps
     if (MODE == GG_SWEEP || MODE == GG_GRAD) {
@@ -406,6 +419,162 @@ gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks the tiles of the launch (unit tile fastest, so that the CTAs running at
+// the same time share A tiles in L2).  The accumulator is double-buffered in TMEM (2 x 256 columns): while the 16
+// epilogue warps (512 threads, 16 units each) drain tile i, the MMA warp already accumulates tile i+1 from a 4-stage
+// TMA ring, so the epilogue of a tile is hidden behind the next tile's MMAs instead of behind a second CTA.
+constexpr int P_STAGES = 4;
+constexpr int P_EPI_WARPS = 16;
+constexpr int P_THREADS = (2 + P_EPI_WARPS) * 32;     // 576
+constexpr int P_SMEM_BYTES = P_STAGES * Cfg::STAGE_BYTES + 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0, const TcRange rng,
+                        int n_jt, int n_nt, int n_tiles) {
+  using C = Cfg;
+  constexpr int JC = C::JC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[P_STAGES], empty_bar[P_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[4 * P_EPI_WARPS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = p.D, H = p.H;
+  const int nkx = (D + BK - 1) / BK;
+  const int nkb = rng.kb_end - rng.kb_begin;
+  (void)H;
+
+  if (MODE == GG_RAWZ && p.done) {
+    if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], P_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;                                   // running k-block counter over all tiles of this CTA
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int j0 = (tile % n_jt) * JC;
+        const int n0 = ((tile / n_jt) % n_nt) * BM;
+        const int tl = tile / (n_jt * n_nt);
+        const int slab = slab0 + tl;
+        for (int li = 0; li < nkb; ++li, ++it) {
+          const int kb = rng.kb_begin + li;
+          const int s = it % P_STAGES;
+          const uint32_t round = it / P_STAGES;
+          if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+          const bool is_x = kb < nkx;
+          const int k0 = (is_x ? kb : kb - nkx) * BK;
+          uint8_t* st = smem + s * C::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES);
+          const CUtensorMap* ma = is_x ? &maps.x : &maps.h;
+          const CUtensorMap* ml = is_x ? &maps.x_lo : &maps.h_lo;
+          tma_load_4d(st, ma, &full_bar[s], 0, k0, n0 / 32, slab);
+          tma_load_4d(st + C::A_BYTES, ml, &full_bar[s], 0, k0, n0 / 32, slab);
+          const CUtensorMap* bh = rng.b_is_grad ? &maps.gx_hi : (is_x ? &maps.wx_hi : &maps.wh_hi);
+          const CUtensorMap* bl = rng.b_is_grad ? &maps.gx_lo : (is_x ? &maps.wx_lo : &maps.wh_lo);
+          const int kb0 = rng.b_is_grad ? li * BK : k0;
+          uint8_t* sb = st + 2 * C::A_BYTES;
+          tma_load_4d(sb, bh, &full_bar[s], 0, kb0, j0 / 32, 0);
+          tma_load_4d(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 32, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, C::NCOL);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t buf = ti & 1, use = ti >> 1;      // `use`-th time this accumulator buffer is filled
+        if (use > 0) {                                   // wait until the epilogue drained its previous contents
+          mbar_wait(&tempty_bar[buf], (use - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + buf * C::NCOL;
+        for (int li = 0; li < nkb; ++li, ++it) {
+          const int s = it % P_STAGES;
+          mbar_wait(&full_bar[s], (it / P_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + C::A_BYTES;
+          const uint32_t b_hi = st + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint32_t off = ks * 1024;
+            umma_tf32(d_tmem, make_desc(a_hi + off), make_desc(b_hi + off), idesc, (li > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32(d_tmem, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
+            umma_tf32(d_tmem, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..17)
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+    const int ugrp = ew >> 2;                          // 4 warps per lane quarter: 16 of the tile's 64 units each
+    const int row = quarter * 32 + lane;
+    float msum[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int j0 = (tile % n_jt) * JC;
+      const int n0 = ((tile / n_jt) % n_nt) * BM;
+      const int tl = tile / (n_jt * n_nt);
+      const uint32_t buf = ti & 1, use = ti >> 1;
+      const int64_t n = (int64_t)n0 + row;
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + buf * C::NCOL + ((uint32_t)(quarter * 32) << 16);
+      epilogue_units<MODE>(p, t_row, ugrp * (JC / 4), (ugrp + 1) * (JC / 4), j0, n, n < p.n, tl, msum);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[buf])) : "memory");
+      }
+    }
+    if (MODE == GG_SWEEP || MODE == GG_GRAD) {
+      double* dst = (MODE == GG_SWEEP) ? p.metrics : p.fw_acc;
+      constexpr int NOUT = (MODE == GG_SWEEP) ? 3 : 4;
+      if (dst) {
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+          const float sm_ = warp_sum(msum[k]);
+          if (lane == 0) red[k * P_EPI_WARPS + ew] = sm_;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const int et = threadIdx.x - 64;
+        if (et < NOUT) {
+          double acc = 0.0;
+#pragma unroll
+          for (int w = 0; w < P_EPI_WARPS; ++w) acc += (double)red[et * P_EPI_WARPS + w];
+          atomicAdd(dst + et, acc);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -425,16 +594,18 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// 3-D fp32 tensor [d2][d1][d0] (d0 contiguous), box 32 x BK x 1, SWIZZLE_128B_ATOM_32B, zero fill out of bounds.
-int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-             uint64_t stride2_elems) {
+// 4-D view of an fp32 tensor [outer][rows][cols] (cols contiguous) for MN-major operand tiles:
+// dims (32 cols-in-chunk, rows, cols/32 chunks, outer), box (32, BK, box_chunks, box_outer), SWIZZLE_128B_ATOM_32B,
+// zero fill out of bounds.  One box lands in shared memory as [outer][chunk][row][32], the canonical MN-major layout.
+int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t outer, uint64_t row_stride_elems,
+             uint64_t outer_stride_elems, uint32_t box_chunks, uint32_t box_outer) {
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADMM_ECUDA; }
-  cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {stride1_elems * 4, stride2_elems * 4};
-  cuuint32_t box[3] = {32, (cuuint32_t)BK, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+  cuuint64_t dims[4] = {32, rows, (cols + 31) / 32, outer};
+  cuuint64_t strides[3] = {row_stride_elems * 4, 128, outer_stride_elems * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)BK, box_chunks, box_outer};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return ADMM_ECUDA; }
@@ -503,14 +674,14 @@ int get_maps(const admm_problem* p, int grad_src, TcMaps* out) {
     const WsLayout w = ws_layout(p);
     const uint64_t ldn = p->ldn, T = p->T, D = p->D, H = p->H;
     int rc = 0;
-    rc |= make_map(&m.x, p->x, ldn, D, T, ldn, D * ldn);
-    rc |= make_map(&m.x_lo, ws + w.x_lo, ldn, D, T, ldn, D * ldn);
-    rc |= make_map(&m.h, p->gate[5], ldn, H, T + 1, ldn, H * ldn);
-    rc |= make_map(&m.h_lo, ws + w.h_lo, ldn, H, T + 1, ldn, H * ldn);
-    rc |= make_map(&m.wx_hi, ws + w.wx_hi, H, D, 4, H, D * H);
-    rc |= make_map(&m.wx_lo, ws + w.wx_lo, H, D, 4, H, D * H);
-    rc |= make_map(&m.wh_hi, ws + w.wh_hi, H, H, 4, H, H * H);
-    rc |= make_map(&m.wh_lo, ws + w.wh_lo, H, H, 4, H, H * H);
+    rc |= make_map(&m.x, p->x, ldn, D, T, ldn, D * ldn, BM / 32, 1);
+    rc |= make_map(&m.x_lo, ws + w.x_lo, ldn, D, T, ldn, D * ldn, BM / 32, 1);
+    rc |= make_map(&m.h, p->gate[5], ldn, H, T + 1, ldn, H * ldn, BM / 32, 1);
+    rc |= make_map(&m.h_lo, ws + w.h_lo, ldn, H, T + 1, ldn, H * ldn, BM / 32, 1);
+    rc |= make_map(&m.wx_hi, ws + w.wx_hi, H, D, 4, H, D * H, Cfg::JC / 32, 4);
+    rc |= make_map(&m.wx_lo, ws + w.wx_lo, H, D, 4, H, D * H, Cfg::JC / 32, 4);
+    rc |= make_map(&m.wh_hi, ws + w.wh_hi, H, H, 4, H, H * H, Cfg::JC / 32, 4);
+    rc |= make_map(&m.wh_lo, ws + w.wh_lo, H, H, 4, H, H * H, Cfg::JC / 32, 4);
     if (rc) return ADMM_ECUDA;
     it = g_maps.emplace(key, m).first;
   }
@@ -519,15 +690,43 @@ int get_maps(const admm_problem* p, int grad_src, TcMaps* out) {
   const WsLayout w = ws_layout(p);
   float* ws = (float*)p->tc_ws;
   const uint64_t K = (grad_src == ADMM_SRC_X) ? p->D : p->H, H = p->H;
-  int rc = make_map(&out->gx_hi, ws + w.g_hi, H, K, 4, H, K * H);
-  rc |= make_map(&out->gx_lo, ws + w.g_lo, H, K, 4, H, K * H);
+  int rc = make_map(&out->gx_hi, ws + w.g_hi, H, K, 4, H, K * H, Cfg::JC / 32, 4);
+  rc |= make_map(&out->gx_lo, ws + w.g_lo, H, K, 4, H, K * H, Cfg::JC / 32, 4);
   return rc ? ADMM_ECUDA : ADMM_OK;
+}
+
+bool use_persistent() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ADMM_TC_PERSISTENT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 template <int MODE>
 int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, int slab0, int tc, const TcRange& rng,
               cudaStream_t st) {
   using C = Cfg;
+  if (use_persistent()) {
+    static bool configured_p = false;
+    if (!configured_p) {
+      cudaFuncSetAttribute(gate_gemm_tc_persistent<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+      configured_p = true;
+    }
+    static int n_sm = 0;
+    if (!n_sm) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_jt = p->H / C::JC, n_nt = (int)(p->ldn / BM);
+    const int n_tiles = n_jt * n_nt * tc;
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    gate_gemm_tc_persistent<MODE><<<grid, P_THREADS, P_SMEM_BYTES, st>>>(a, maps, slab0, rng, n_jt, n_nt, n_tiles);
+    count_launch();
+    return check_launch("gate_gemm_tc_persistent");
+  }
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(gate_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);

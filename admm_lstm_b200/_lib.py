@@ -39,7 +39,7 @@ class Problem(C.Structure):
         ("a", C.c_void_p), ("dual_y", C.c_void_p),
         ("wx", C.c_void_p), ("wh", C.c_void_p), ("wy", C.c_void_p),
         ("tc_ws", C.c_void_p), ("tc_ws_bytes", C.c_int64),
-        ("zstore", C.c_void_p), ("wx_prev", C.c_void_p),
+        ("zstore", C.c_void_p), ("wx_prev", C.c_void_p), ("z_valid", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

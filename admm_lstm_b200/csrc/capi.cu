@@ -107,6 +107,7 @@ int admm_forward_t(const admm_problem* p, int t, void* stream) {
   ADMM_REQUIRE(t >= 1 && t <= p->T, "admm_forward_t: t=%d out of 1..%d", t, p->T);
   cudaStream_t st = (cudaStream_t)stream;
   GateGemmArgs a = base_args(p, t);
+  if (p->tc_ws && tc_eligible(p) && p->zstore) { a.zstore = p->zstore; a.zT = p->T; a.zt0 = t - 1; }
   rc = run_gate_gemm(GG_FORWARD, p, a, 1, st);
   if (rc) return rc;
   if (t == p->T && p->a)
@@ -181,7 +182,18 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
     a.zstore = p->zstore; a.zT = p->T; a.zt0 = t0;
     a.z_accumulate = (src == ADMM_SRC_H);
   }
-  rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
+  if (use_tc && p->zstore && p->wx_prev && src == ADMM_SRC_X && p->z_valid) {
+    // the previous sweep (or the forward initialisation) left z of the current weights and states in zstore:
+    // no GEMM, one streaming pass
+    GradFromZArgs e;
+    e.n = p->n; e.ldn = p->ldn; e.H = p->H; e.tc = tc; e.zT = p->T; e.zt0 = t0; e.zstore = p->zstore;
+    for (int g = 0; g < 4; ++g) { e.gate[g] = a.gate[g]; e.dual[g] = a.dual[g]; e.rho[g] = p->hp.rho[g]; }
+    e.s_tstride = a.s_tstride;
+    e.r = a.scratch; e.r_lo = a.scratch_q; e.fw_acc = fw_acc;
+    rc = grad_from_z(e, st);
+  } else {
+    rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
+  }
   if (rc) return rc;
   AtrArgs r;
   r.ldn = p->ldn; r.H = p->H; r.tc = tc;
@@ -292,6 +304,8 @@ int admm_sweep_t(const admm_problem* p, int t, double* metrics, void* stream) {
   GateGemmArgs a = base_args(p, t);
   a.last = (t == p->T);
   a.metrics = metrics;
+  // keep z_t: it is the pre-activation the next iteration's x-phase gradient starts from (admm_problem::z_valid)
+  if (p->tc_ws && tc_eligible(p) && p->zstore) { a.zstore = p->zstore; a.zT = p->T; a.zt0 = t - 1; }
   return run_gate_gemm(GG_SWEEP, p, a, 1, (cudaStream_t)stream);
 }
 

@@ -77,4 +77,20 @@ struct ProbeEvalArgs {
 };
 int probe_eval(const ProbeEvalArgs& a, cudaStream_t st);
 
+// x-phase gradient residual from stored pre-activations (grad_from_z.cu): R^T, its tf32 low part and f(w).
+struct GradFromZArgs {
+  int64_t n, ldn;
+  int32_t H, tc;
+  int32_t zT, zt0;        // zstore is [4][H][zT][ldn]; first timestep (0-based) of the chunk
+  const float* zstore;
+  const float* gate[4];   // gate_g / lambda_g slabs of the first timestep of the chunk
+  const float* dual[4];
+  int64_t s_tstride;
+  float rho[4];
+  float* r;               // [4][H][tc][ldn]
+  float* r_lo;
+  double* fw_acc;         // [4]
+};
+int grad_from_z(const GradFromZArgs& a, cudaStream_t st);
+
 }  // namespace admm

@@ -185,6 +185,11 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
             const ForwardResult r = forward_point<FastMath>(z[0][eb + e], z[1][eb + e], z[2][eb + e], z[3][eb + e], cp[e]);
+            if (p.zstore) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, z[g][eb + e]);
+            }
             if (p.gate[0]) __stcs(p.gate[0] + off[e], r.i);
             if (p.gate[1]) __stcs(p.gate[1] + off[e], r.f);
             if (p.gate[2]) __stcs(p.gate[2] + off[e], r.g);
@@ -237,6 +242,11 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             }
             __stcs(p.dual[0] + off[e], r.li); __stcs(p.dual[1] + off[e], r.lf); __stcs(p.dual[2] + off[e], r.lg);
             __stcs(p.dual[3] + off[e], r.lo); __stcs(p.dual[4] + off[e], r.lc);
+            if (p.zstore) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, z[g][eb + e]);
+            }
             if (ok) { msum[0] += r.prim_sq; msum[1] += r.dual_sq; msum[2] += r.penalty; }
           }
         }

@@ -24,22 +24,37 @@ constexpr int NT = 256;
 constexpr int JB = 8;          // hidden units per block
 constexpr int NCS = ADMM_FK_SLOTS;
 
-template <int NC, bool IS_G>
+// Residual of one element for one candidate.  The instruction stream is what bounds this kernel (ncu: issue slots
+// 69 % busy, XU pipe 56 %, at 22 instructions per activation before this was flattened), so the sigmoid path is
+// spelled out: FFMA, FMNMX, FMUL, MUFU.EX2, FADD, MUFU.RCP, 2 FFMA (Newton), 2 FADD, FFMA = 11 issue slots.
+template <bool IS_G>
+__device__ __forceinline__ float probe_term(float z, float lr, float gv) {
+  const float a = IS_G ? FastMath::tanh(z) : FastMath::sigmoid(z);
+  return (a - lr) - gv;                 // the reference's association (admm.py:319-323)
+}
+
+// NSLOT accumulators: candidates [0, NC) at theta = 2^-(kbase + k) and, if WITH_FW, slot NC at Q = 0 (= f(w)).
+// FULL = all four samples of the thread are real (no ghost-row masking).
+template <int NC, bool WITH_FW, bool IS_G, bool FULL>
 __device__ __forceinline__ void accumulate(const float4& z4, const float4& q4, const float4& lam4, const float4& gv4,
-                                           float rho, const float (&inv_theta)[NC], const bool (&ok)[4],
-                                           float (&acc)[NC + 1]) {
+                                           float rho, float inv_rho, bool rho_pow2, const float (&inv_theta)[NC],
+                                           const float (&mask)[4], float (&acc)[NC + (WITH_FW ? 1 : 0)]) {
   const float z[4] = {z4.x, z4.y, z4.z, z4.w}, q[4] = {q4.x, q4.y, q4.z, q4.w};
   const float lam[4] = {lam4.x, lam4.y, lam4.z, lam4.w}, gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    if (!ok[e]) continue;
-    const float lr = lam[e] / rho;
+    // lambda / rho: exact through the reciprocal when rho is a power of two (every shipped gate rho is 1)
+    const float lr = rho_pow2 ? lam[e] * inv_rho : __fdiv_rn(lam[e], rho);
 #pragma unroll
-    for (int k = 0; k <= NC; ++k) {
-      const float zz = (k < NC) ? fmaf(q[e], inv_theta[k], z[e]) : z[e];
-      const float a = IS_G ? FastMath::tanh(zz) : FastMath::sigmoid(zz);
-      const float u = (a - lr) - gv[e];
+    for (int k = 0; k < NC; ++k) {
+      float u = probe_term<IS_G>(fmaf(q[e], inv_theta[k], z[e]), lr, gv[e]);
+      if (!FULL) u *= mask[e];
       acc[k] = fmaf(u, u, acc[k]);
+    }
+    if (WITH_FW) {
+      float u = probe_term<IS_G>(z[e], lr, gv[e]);
+      if (!FULL) u *= mask[e];
+      acc[NC] = fmaf(u, u, acc[NC]);
     }
   }
 }
@@ -47,9 +62,10 @@ __device__ __forceinline__ void accumulate(const float4& z4, const float4& q4, c
 // Work item = (gate g, timestep tl, block of JB units, block of 4*NT samples).  The grid is a fixed number of
 // CTAs that stride over the items: a launch whose gates are all decided (the speculative later passes of the
 // backtracking) then costs a few hundred CTAs that exit at once instead of one CTA per item.
-template <int NC>
+template <int NC, bool WITH_FW>
 __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, int n_jb, int n_nb, int64_t n_items) {
-  __shared__ float red[(NC + 1) * (NT / 32)];
+  constexpr int NSLOT = NC + (WITH_FW ? 1 : 0);
+  __shared__ float red[NSLOT * (NT / 32)];
   if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -63,39 +79,48 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
     if (nc <= 0) continue;
     float inv_theta[NC];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) inv_theta[k] = (k < nc) ? ldexpf(1.0f, -(kbase + k)) : 0.f;
+    for (int k = 0; k < NC; ++k) inv_theta[k] = (k < nc) ? __int_as_float((127 - (kbase + k)) << 23) : 0.f;   // 2^-(kbase+k), kbase+k < 64
     const int64_t n = ((int64_t)nb * NT + threadIdx.x) * 4;
     const int j0 = jb * JB;
-    float acc[NC + 1];
+    float acc[NSLOT];
 #pragma unroll
-    for (int k = 0; k <= NC; ++k) acc[k] = 0.f;
+    for (int k = 0; k < NSLOT; ++k) acc[k] = 0.f;
     const float rho = p.rho[g];
+    const float inv_rho = 1.0f / rho;
+    const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
+    const bool block_full = ((int64_t)(nb + 1) * NT * 4 <= p.n);       // uniform over the CTA
     if (n < p.ldn) {
-      const bool ok[4] = {n + 0 < p.n, n + 1 < p.n, n + 2 < p.n, n + 3 < p.n};
+      const float mask[4] = {n + 0 < p.n ? 1.f : 0.f, n + 1 < p.n ? 1.f : 0.f, n + 2 < p.n ? 1.f : 0.f,
+                             n + 3 < p.n ? 1.f : 0.f};
       const float* gate = p.gate[g] + (int64_t)tl * p.s_tstride + n;
       const float* dual = p.dual[g] + (int64_t)tl * p.s_tstride + n;
+      const int jend = (p.H - j0 < JB) ? p.H - j0 : JB;
 #pragma unroll 2
-      for (int jj = 0; jj < JB; ++jj) {
+      for (int jj = 0; jj < jend; ++jj) {
         const int j = j0 + jj;
-        if (j >= p.H) break;
         const int64_t so = (((int64_t)g * p.H + j) * p.tc + tl) * p.ldn + n;
         const int64_t zo = (((int64_t)g * p.H + j) * p.z_T + p.z_t0 + tl) * p.ldn + n;
         const float4 z4 = ld_stream(p.z0 + zo), q4 = ld_stream(p.q + so);
         const float4 lam4 = ld_stream(dual + (int64_t)j * p.ldn), gv4 = ld_stream(gate + (int64_t)j * p.ldn);
-        if (g == 2) accumulate<NC, true>(z4, q4, lam4, gv4, rho, inv_theta, ok, acc);
-        else accumulate<NC, false>(z4, q4, lam4, gv4, rho, inv_theta, ok, acc);
+        if (g == 2) {
+          if (block_full) accumulate<NC, WITH_FW, true, true>(z4, q4, lam4, gv4, rho, inv_rho, rho_pow2, inv_theta, mask, acc);
+          else accumulate<NC, WITH_FW, true, false>(z4, q4, lam4, gv4, rho, inv_rho, rho_pow2, inv_theta, mask, acc);
+        } else {
+          if (block_full) accumulate<NC, WITH_FW, false, true>(z4, q4, lam4, gv4, rho, inv_rho, rho_pow2, inv_theta, mask, acc);
+          else accumulate<NC, WITH_FW, false, false>(z4, q4, lam4, gv4, rho, inv_rho, rho_pow2, inv_theta, mask, acc);
+        }
       }
     }
-    // slots beyond nc were evaluated at Q*0 (= f(w)); only slots < nc and, for the window, the f(w) slot are published
+    // slots in [nc, NC) were evaluated at Q*0 and are not published
 #pragma unroll
-    for (int k = 0; k <= NC; ++k) {
+    for (int k = 0; k < NSLOT; ++k) {
       const float s = warp_sum(acc[k]);
       if (lane == 0) red[k * (NT / 32) + warp] = s;
     }
     __syncthreads();
-    if (threadIdx.x <= NC) {
+    if (threadIdx.x < NSLOT) {
       const int k = threadIdx.x;
-      if (k < nc || (k == NC && p.publish_fw)) {
+      if (k < nc || k == NC) {
         double s = 0.0;
         for (int w = 0; w < NT / 32; ++w) s += (double)red[k * (NT / 32) + w];
         const int slot = (k == NC) ? ADMM_MAX_CAND : p.slot0[g] + k;
@@ -104,6 +129,12 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
     }
     __syncthreads();
   }
+}
+
+template <int NC>
+void launch_probe_eval(const ProbeEvalArgs& a, unsigned grid, int n_jb, int n_nb, int64_t n_items, cudaStream_t st) {
+  if (a.publish_fw) probe_eval_kernel<NC, true><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
+  else probe_eval_kernel<NC, false><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
 }
 
 }  // namespace
@@ -116,9 +147,12 @@ int probe_eval(const ProbeEvalArgs& a, cudaStream_t st) {
   if (nc <= 0 || n_jb <= 0) return ADMM_OK;
   const int64_t n_items = (int64_t)n_nb * n_jb * 4 * a.tc;
   const unsigned grid = (unsigned)(n_items < 148 * 8 ? n_items : 148 * 8);
-  if (nc <= 8) probe_eval_kernel<8><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
-  else if (nc <= 16) probe_eval_kernel<16><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
-  else probe_eval_kernel<ADMM_MAX_CAND><<<grid, NT, 0, st>>>(a, n_jb, n_nb, n_items);
+  if (nc <= 4) launch_probe_eval<4>(a, grid, n_jb, n_nb, n_items, st);
+  else if (nc <= 8) launch_probe_eval<8>(a, grid, n_jb, n_nb, n_items, st);
+  else if (nc <= 12) launch_probe_eval<12>(a, grid, n_jb, n_nb, n_items, st);
+  else if (nc <= 16) launch_probe_eval<16>(a, grid, n_jb, n_nb, n_items, st);
+  else if (nc <= 24) launch_probe_eval<24>(a, grid, n_jb, n_nb, n_items, st);
+  else launch_probe_eval<ADMM_MAX_CAND>(a, grid, n_jb, n_nb, n_items, st);
   count_launch();
   return check_launch("probe_eval");
 }

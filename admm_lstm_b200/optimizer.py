@@ -225,6 +225,7 @@ class ADMMBasedOptimizer(object):
         self.last_metrics: Optional[Dict[str, float]] = None
         self.phase_events = None          # set by enable_phase_timing()
         self.__initialize_primal_gates()
+        self._set_z_valid(True)           # the forward pass stored z of the initial weights and states
 
     # ------------------------------------------------------------------------------------ setup
     def __initialize_training_constants(self, train_x, train_y) -> Tuple[int, int, int, int, int]:
@@ -282,6 +283,11 @@ class ADMMBasedOptimizer(object):
             self._call("admm_forward_t", self._pp, t, st)
 
     # ------------------------------------------------------------------------------------ weights
+    def _set_z_valid(self, valid: bool) -> None:
+        """zstore holds z = x W + h U of the current inputs, states and weights for every t (admm_problem::z_valid):
+        true after the forward initialisation and after every complete sweep, false once anything else wrote them."""
+        self._p.z_valid = int(bool(valid) and self._zstore is not None)
+
     def _param_names(self):
         return [f"{s}2{g}" for g in _GATES for s in ("x", "h")] + ["out"]
 
@@ -309,6 +315,7 @@ class ADMMBasedOptimizer(object):
             if getattr(self.model, name).data_ptr() != self._bound_ptrs[name]:
                 self._pull_weights_from_model()
                 self._bind_weights_to_model()
+                self._set_z_valid(False)
                 if self._tc_ws is not None:
                     self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS, _stream_ptr())
                 return
@@ -347,11 +354,14 @@ class ADMMBasedOptimizer(object):
         yd = train_y.to(self.device, non_blocking=True)
         self._x[:, :, :n].copy_(xd.permute(1, 2, 0))
         self._y[:, :n].copy_(yd.t())
+        self._set_z_valid(False)
         if self._tc_ws is not None:
             self._call("admm_tc_refresh", self._pp, _lib.TC_INPUTS, _stream_ptr())
 
     def state_changed(self) -> None:
-        """Call after writing the state buffers directly (tests do): re-derives the tensor-core side buffers."""
+        """Call after writing the state or weight buffers directly (tests do): re-derives the tensor-core side
+        buffers and drops the stored pre-activations."""
+        self._set_z_valid(False)
         if self._tc_ws is not None:
             self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS | _lib.TC_STATE, _stream_ptr())
 
@@ -440,6 +450,7 @@ class ADMMBasedOptimizer(object):
         self._metrics.zero_()
         for t in range(1, self.seq_len + 1):
             self._call("admm_sweep_t", pp, t, self._metrics.data_ptr(), st)
+        self._set_z_valid(True)           # the sweep's GEMMs left z of the new weights / states in zstore
         self._mark("sweep")
         self.__update_last(st)
         self._mark("last")

@@ -99,6 +99,12 @@ typedef struct admm_problem {
    * x2g taken before its update, from which the h-phase refreshes zstore with x (W_new - W_old) only. */
   float* zstore;
   float* wx_prev;
+  /* Set by the caller when zstore holds z = x W + h U of the CURRENT x, h, wx, wh for every timestep -- true after
+   * the forward initialisation or a complete sweep t = 1..T (both write zstore from the GEMM they run anyway), false
+   * after anything else changed inputs, state or weights.  When set, the x-phase gradient pass of the next step runs
+   * no GEMM at all: it is an elementwise pass over zstore. */
+  int32_t z_valid;
+  int32_t reserved_;
 } admm_problem;
 
 /* Slots of the fp64 metric accumulator filled by admm_sweep_t / admm_last_apply. */

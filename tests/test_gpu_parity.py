@@ -431,3 +431,26 @@ def test_tensor_core_step_vs_oracle(variant, shape, params):
         ora.step()
         opt.step()
         _cmp_state(opt, ora, params, f"tc step{s}")
+
+
+def test_stored_preactivations_equal_recomputed():
+    """The x-phase gradient from the z the previous sweep stored (admm_problem::z_valid, grad_from_z.cu) must give
+    the same iterates as recomputing z with the gate GEMM: same kernel main loop, same inputs -> same bits."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    n, t, d, h, o = 700, 5, 16, 128, 1
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=5)
+    _, a = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    _, b = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    assert a.keeps_preactivations and a._p.z_valid == 1
+    for _ in range(4):
+        a.step()
+        assert a._p.z_valid == 1
+        b._set_z_valid(False)          # force the GEMM path
+        b.step()
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert np.array_equal(wa[k], wb[k]), k
+    for k in ("i", "f", "g", "o", "c", "h"):
+        assert torch.equal(a.gates[k], b.gates[k]), k
+    assert a.theta_trace() == b.theta_trace()

@@ -47,7 +47,20 @@ class ProbePlan(C.Structure):
     _fields_ = [("k0", C.c_int32 * 4), ("ncand", C.c_int32), ("proof", C.c_int32)]
 
 
+class LHyper(C.Structure):
+    _fields_ = [("rho_s", C.c_float), ("rho_p", C.c_float), ("rho9", C.c_float), ("rho10", C.c_float),
+                ("rho11", C.c_float), ("lam_w", C.c_float), ("lam_u", C.c_float), ("lam_y", C.c_float),
+                ("n_norm", C.c_float)]
+
+
+class LProblem(C.Structure):
+    """admm_l_problem (ADMM-LSTM-L): `base` first, so a pointer to it is also a valid admm_problem*."""
+    _fields_ = [("base", Problem), ("z", C.c_void_p * 4), ("lam_s", C.c_void_p * 4), ("lam_p", C.c_void_p * 4),
+                ("lam9", C.c_void_p), ("lam10", C.c_void_p), ("hp", LHyper)]
+
+
 PP = C.POINTER(Problem)
+LPP = C.POINTER(LProblem)
 PLAN = C.POINTER(ProbePlan)
 vp = C.c_void_p
 
@@ -75,6 +88,17 @@ SIGNATURES = {
     "admm_tc_refresh": (C.c_int, [PP, C.c_int, vp]),
     "admm_debug_preact": (C.c_int, [PP, C.c_int, vp, C.c_int, vp]),
     "admm_launch_count": (C.c_int64, [C.c_int]),
+    # ADMM-LSTM-L
+    "admm_l_sizeof_problem": (C.c_int, []),
+    "admm_l_forward_t": (C.c_int, [LPP, C.c_int, vp, vp]),
+    "admm_l_output": (C.c_int, [LPP, vp]),
+    "admm_l_sums": (C.c_int, [LPP, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "admm_l_gram_xx": (C.c_int, [LPP, vp, vp]),
+    "admm_l_sums_last": (C.c_int, [LPP, vp, vp, vp]),
+    "admm_l_sweep_max": (C.c_int, [LPP, C.c_int, vp, vp, vp]),
+    "admm_l_sweep_gates": (C.c_int, [LPP, C.c_int, vp, vp, vp, vp]),
+    "admm_l_sweep_cell": (C.c_int, [LPP, C.c_int, vp, vp, vp, vp]),
+    "admm_l_last": (C.c_int, [LPP, vp, vp, vp, vp]),
 }
 
 _lib = None
@@ -102,6 +126,8 @@ def load():
         raise AdmmLibraryError("ABI version mismatch between _lib.py and the shared library")
     if lib.admm_sizeof_problem() != C.sizeof(Problem):
         raise AdmmLibraryError("admm_problem layout mismatch between _lib.py and the shared library")
+    if lib.admm_l_sizeof_problem() != C.sizeof(LProblem):
+        raise AdmmLibraryError("admm_l_problem layout mismatch between _lib.py and the shared library")
     _lib = lib
     return lib
 

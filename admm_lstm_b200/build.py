@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libadmm_lstm_b200.so")
 HOSTLIB = os.path.join(PKG, "libadmm_point_math_host.so")
-SOURCES = ["capi.cu", "gate_gemm_simt.cu", "atr_simt.cu", "small_kernels.cu", "gate_gemm_tc.cu", "probe_eval.cu", "grad_from_z.cu"]
+SOURCES = ["capi.cu", "gate_gemm_simt.cu", "atr_simt.cu", "small_kernels.cu", "gate_gemm_tc.cu", "probe_eval.cu", "grad_from_z.cu", "admm_l.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

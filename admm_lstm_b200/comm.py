@@ -25,6 +25,13 @@ class Comm:
         for t in tensors:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def allreduce_max_(self, *tensors: torch.Tensor) -> None:
+        """In-place maximum over ranks (the global torch.max scalars of ADMM-LSTM-L, admm_lstm.py:168,179,225)."""
+        if not self.active:
+            return
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
     def shard_range(self, n_total: int) -> Tuple[int, int]:
         """Contiguous, balanced slice [lo, hi) of n_total samples owned by this rank."""
         base, rem = divmod(n_total, self.world_size)

@@ -1,0 +1,488 @@
+// admm_l.cu -- ADMM-LSTM-L: kernels and C ABI.
+//
+// Reference: /root/reference/comparison_experiment/admm_l/admm_lstm.py (update functions), driven by
+// admm_l/main.py:139-191.  Differences in HOW, not WHAT:
+//  * weight phase: the residual -z_t + x_t W + h_{t-1} U - lambda_t/rho is linear in W and U (admm_lstm.py:107-163), so
+//    the eight updates need only Gram / right-hand-side sums over samples x timesteps.  They come from ONE packing pass
+//    (V_g = z_g + lambda_g/rho and h_{t-1}, five row groups) and two runs of the A^T R reduction GEMM of the main path
+//    (tcgen05 3xTF32, fp64 accumulation across chunks); the reference re-runs 2T GEMMs per backtracking probe.
+//  * sweep: one gate GEMM per timestep (the reference recomputes x W + h U eight times per timestep) and three
+//    elementwise kernels separated by the algorithm's own global reductions (torch.max in update_z / update_zg /
+//    update_c and fro_qua(o), admm_lstm.py:168,179,225,230), which are also where sample shards must exchange scalars.
+// Ghost rows (n >= N) are never touched and stay zero, so no sum needs masking.
+#include <string.h>
+
+#include "common.cuh"
+#include "gate_gemm.h"
+#include "small_kernels.h"
+#include "tc_path.h"
+
+namespace admm {
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float l_sig(float x) { return 1.0f / (1.0f + expf(-x)); }   // torch.sigmoid
+__device__ __forceinline__ float appro_sig(float m) { return 0.5f * (1.0f + m) + 0.125f; }   // admm_lstm.py:169
+__device__ __forceinline__ float appro_tanh(float m) { return 2.0f * (1.0f + m) + 2.0f; }    // admm_lstm.py:180,226
+
+// Slabs of one slot s (all [H][ldn]) plus the scalars.
+struct LSlot {
+  int64_t n, ldn;
+  int32_t H;
+  float* gate[6];        // i f g o c h at slot s
+  const float* c_prev;   // c at slot s-1
+  float* z[4];
+  float* lam_s[4];
+  float* lam_p[4];
+  float* lam9;
+  float* lam10;
+  const float* P;        // [4][H][ldn] = x W + h_{s-1} U
+  float* h_lo;           // tf32 low part of h at slot s, or nullptr
+  admm_l_hyper hp;
+};
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float m = 0.f;
+  for (int w = 0; w < NT / 32; ++w) m = fmaxf(m, red[w]);
+  return m;
+}
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+  atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));     // bit order == value order for v >= 0
+}
+
+// ---------------------------------------------------------------------------------------------------- forward
+// main.py:89-100 from P: z, gates, c, h
+__global__ void __launch_bounds__(NT) l_forward_kernel(const LSlot p) {
+  const int64_t total = (int64_t)p.H * p.ldn;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    const int64_t n = idx % p.ldn;
+    if (n >= p.n) continue;
+    float zz[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { zz[g] = p.P[(int64_t)g * total + idx]; p.z[g][idx] = zz[g]; }
+    const float i = l_sig(zz[0]), f = l_sig(zz[1]), gg = tanhf(zz[2]), o = l_sig(zz[3]);
+    const float c = f * p.c_prev[idx] + i * gg;
+    const float h = o * tanhf(c);
+    p.gate[0][idx] = i; p.gate[1][idx] = f; p.gate[2][idx] = gg; p.gate[3][idx] = o;
+    p.gate[4][idx] = c; p.gate[5][idx] = h;
+    if (p.h_lo) p.h_lo[idx] = tf32_lo(h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- packing
+// rows [0,4H): V_g = z_g + lambda_s,g / rho_s ; rows [4H,5H): h_{t-1}; each with its tf32 low part.
+struct LPack {
+  int64_t n, ldn;
+  int32_t H, tc, t0;      // timesteps t0 .. t0+tc-1 (0-based) = slots t0+1 ..
+  const float* z[4];      // full tensors [T+1][H][ldn]
+  const float* lam_s[4];
+  const float* h;
+  float rho_s;
+  float* r;               // [5H][tc][ldn]
+  float* r_lo;
+};
+__global__ void __launch_bounds__(NT) l_pack_kernel(const LPack p) {
+  const int64_t per_t = (int64_t)p.H * p.ldn;
+  const int64_t total = per_t * p.tc;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    const int tl = (int)(idx / per_t);
+    const int64_t rem = idx % per_t;
+    const int j = (int)(rem / p.ldn);
+    const int64_t n = rem % p.ldn;
+    const bool ok = n < p.n;
+    const int64_t so = (int64_t)(p.t0 + tl + 1) * per_t + rem;         // slot of timestep t
+    const int64_t sp = (int64_t)(p.t0 + tl) * per_t + rem;             // slot of h_{t-1}
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float v = ok ? p.z[g][so] + p.lam_s[g][so] / p.rho_s : 0.f;
+      const int64_t ro = (((int64_t)g * p.H + j) * p.tc + tl) * p.ldn + n;
+      p.r[ro] = v;
+      p.r_lo[ro] = tf32_lo(v);
+    }
+    const float hv = ok ? p.h[sp] : 0.f;
+    const int64_t ro = (((int64_t)4 * p.H + j) * p.tc + tl) * p.ldn + n;
+    p.r[ro] = hv;
+    p.r_lo[ro] = tf32_lo(hv);
+  }
+}
+
+// p_t[j] += sum_n h_T[j][n] (a[n] + lambda11[n]/rho11)     (eq1_W, admm_lstm.py:76-81, the a + lambda/rho part)
+__global__ void __launch_bounds__(NT) l_pt_kernel(const float* hT, const float* a, const float* lam11, float rho11,
+                                                  int64_t n, int64_t ldn, double* p_t) {
+  __shared__ double red[NT / 32];
+  const int j = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += NT) acc += (double)hT[(int64_t)j * ldn + i] * (double)(a[i] + lam11[i] / rho11);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < NT / 32; ++w) s += red[w];
+    atomicAdd(p_t + j, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- sweep
+// red_max[g] = max |gate_g - lambda_p,g / rho_p|          (admm_lstm.py:168, 179)
+__global__ void __launch_bounds__(NT) l_max_kernel(const LSlot p, float* red_max) {
+  __shared__ float red[NT / 32];
+  const int64_t total = (int64_t)p.H * p.ldn;
+  float m[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    if (idx % p.ldn >= p.n) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) m[g] = fmaxf(m[g], fabsf(p.gate[g][idx] - p.lam_p[g][idx] / p.hp.rho_p));
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float b = block_max(m[g], red);
+    if (threadIdx.x == 0) atomic_max_nonneg(red_max + g, b);
+  }
+}
+
+// update_z / update_zg (admm_lstm.py:166-188)
+__device__ __forceinline__ float l_update_z(float z, float out, float P, float lam1, float lam2, float rs, float rp,
+                                            float appro, bool is_g) {
+  const float act = is_g ? tanhf(z) : l_sig(z);
+  const float der = is_g ? 1.0f - act * act : act * (1.0f - act);
+  const float form1 = P - lam1 / rs;
+  const float form2 = rp * (act - out + lam2 / rp) * der;
+  const float form3 = rs * form1 + 0.5f * rp * appro * z - form2;
+  return 2.0f * form3 / (2.0f * rs + rp * appro);
+}
+
+// z_f,f, z_i,i, z_o,o, z_g,g (main.py:150-165) + the reductions update_c needs
+__global__ void __launch_bounds__(NT) l_gates_kernel(const LSlot p, float* red_max, double* red_sum) {
+  __shared__ float red[NT / 32];
+  __shared__ double redd[NT / 32];
+  const int64_t total = (int64_t)p.H * p.ldn;
+  const float rs = p.hp.rho_s, rp = p.hp.rho_p, r9 = p.hp.rho9, r10 = p.hp.rho10;
+  const float ap_i = appro_sig(red_max[0]), ap_f = appro_sig(red_max[1]), ap_g = appro_tanh(red_max[2]),
+              ap_o = appro_sig(red_max[3]);
+  float mx = 0.f, so2 = 0.f;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    if (idx % p.ldn >= p.n) continue;
+    const float Pi = p.P[idx], Pf = p.P[total + idx], Pg = p.P[2 * total + idx], Po = p.P[3 * total + idx];
+    float i = p.gate[0][idx], f = p.gate[1][idx], g = p.gate[2][idx], o = p.gate[3][idx];
+    const float ct = p.gate[4][idx], h = p.gate[5][idx], c_ = p.c_prev[idx];
+    const float l9 = p.lam9[idx], l10 = p.lam10[idx];
+    const float lpi = p.lam_p[0][idx], lpf = p.lam_p[1][idx], lpg = p.lam_p[2][idx], lpo = p.lam_p[3][idx];
+    // f
+    const float zf = l_update_z(p.z[1][idx], f, Pf, p.lam_s[1][idx], lpf, rs, rp, ap_f, false);
+    f = (rp * (l_sig(zf) + lpf / rp) + r9 * c_ * (ct - g * i + l9 / r9)) / (rp + r9 * c_ * c_);          // :191-196
+    // i
+    const float zi = l_update_z(p.z[0][idx], i, Pi, p.lam_s[0][idx], lpi, rs, rp, ap_i, false);
+    i = (rp * (l_sig(zi) + lpi / rp) + r9 * g * (ct - c_ * f + l9 / r9)) / (rp + r9 * g * g);            // :199-204
+    // o
+    const float zo = l_update_z(p.z[3][idx], o, Po, p.lam_s[3][idx], lpo, rs, rp, ap_o, false);
+    const float tc = tanhf(ct);
+    o = (rp * (l_sig(zo) + lpo / rp) + r10 * tc * (h - l10 / r10)) / (rp + r10 * tc * tc);               // :207-212
+    // g
+    const float zg = l_update_z(p.z[2][idx], g, Pg, p.lam_s[2][idx], lpg, rs, rp, ap_g, true);
+    g = (rp * (tanhf(zg) + lpg / rp) + r9 * i * (ct - c_ * f + l9 / r9)) / (rp + r9 * i * i);            // :215-220
+    p.z[0][idx] = zi; p.z[1][idx] = zf; p.z[2][idx] = zg; p.z[3][idx] = zo;
+    p.gate[0][idx] = i; p.gate[1][idx] = f; p.gate[2][idx] = g; p.gate[3][idx] = o;
+    mx = fmaxf(mx, fabsf((h - l10 / r10) * 1.0f / o));                                                  // :225
+    so2 = fmaf(o, o, so2);                                                                              // :230
+  }
+  const float bm = block_max(mx, red);
+  double s = warp_sum((double)so2);
+  if ((threadIdx.x & 31) == 0) redd[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomic_max_nonneg(red_max + 4, bm);
+    double t = 0.0;
+    for (int w = 0; w < NT / 32; ++w) t += redd[w];
+    atomicAdd(red_sum, t);
+  }
+}
+
+// The ten dual updates of one element (admm_lstm.py:274-311, main.py:170-188)
+__device__ __forceinline__ void l_duals(const LSlot& p, int64_t idx, int64_t total, float c, float h, float c_) {
+  const float rs = p.hp.rho_s, rp = p.hp.rho_p, r9 = p.hp.rho9, r10 = p.hp.rho10;
+  const float i = p.gate[0][idx], f = p.gate[1][idx], g = p.gate[2][idx], o = p.gate[3][idx];
+  p.lam10[idx] = p.lam10[idx] + r10 * (tanhf(c) * o - h);
+  p.lam9[idx] = p.lam9[idx] + r9 * (c - g * i - c_ * f);
+  const float gv[4] = {i, f, g, o};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float z = p.z[q][idx];
+    const float act = (q == 2) ? tanhf(z) : l_sig(z);
+    p.lam_p[q][idx] = p.lam_p[q][idx] + rp * (act - gv[q]);
+    p.lam_s[q][idx] = p.lam_s[q][idx] + rs * (z - p.P[(int64_t)q * total + idx]);
+  }
+}
+
+// update_c (:223-241), update_h for s < T (:249-250), then the duals.  LAST: c only.
+template <bool LAST>
+__global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* red_max, const double* red_sum) {
+  const int64_t total = (int64_t)p.H * p.ldn;
+  const float r9 = p.hp.rho9, r10 = p.hp.rho10;
+  const float appro_h = appro_tanh(red_max[4]);
+  const float qua_o = (float)red_sum[0];
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    if (idx % p.ldn >= p.n) continue;
+    const float i = p.gate[0][idx], f = p.gate[1][idx], g = p.gate[2][idx], o = p.gate[3][idx];
+    const float ct = p.gate[4][idx], h = p.gate[5][idx], c_ = p.c_prev[idx];
+    const float l9 = p.lam9[idx], l10 = p.lam10[idx];
+    const float form1 = r9 * (g * i + c_ * f - l9 / r9);
+    const float tc = tanhf(ct);
+    const float form2 = r10 * (tc * o - h + l10 / r10) * (1.0f - tc * tc) * o;
+    const float form3 = 0.5f * r10 * qua_o * ct * appro_h;
+    const float form4 = r9 + 0.5f * r10 * qua_o * appro_h;
+    const float c = (form1 - form2 + form3) / form4;
+    p.gate[4][idx] = c;
+    if (!LAST) {
+      const float hn = (r10 * (tanhf(c) * o + l10 / r10)) / r10;
+      p.gate[5][idx] = hn;
+      if (p.h_lo) p.h_lo[idx] = tf32_lo(hn);
+      l_duals(p, idx, total, c, hn, c_);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- t = T-1
+// tmp[n] = Form10 = -a + h Wy - lambda11/rho11     (update_h, :252)
+__global__ void __launch_bounds__(NT) l_form10_kernel(const float* h, const float* wy, const float* a, const float* lam11,
+                                                      float rho11, int64_t n, int64_t ldn, int H, float* tmp) {
+  const int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+  if (i >= n) return;
+  float d = 0.f;
+  for (int j = 0; j < H; ++j) d = fmaf(h[(int64_t)j * ldn + i], wy[j], d);
+  tmp[i] = -a[i] + d - lam11[i] / rho11;
+}
+// h_T = (Form1 - rho11 Form11 + theta h)/(rho10 + theta)   (:258)
+__global__ void __launch_bounds__(NT) l_last_h_kernel(const LSlot p, const float* wy, const float* tmp, const float* theta_h) {
+  const int64_t total = (int64_t)p.H * p.ldn;
+  const float th = theta_h[0], r10 = p.hp.rho10, r11 = p.hp.rho11;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    const int64_t n = idx % p.ldn;
+    if (n >= p.n) continue;
+    const int j = (int)(idx / p.ldn);
+    const float form1 = r10 * (tanhf(p.gate[4][idx]) * p.gate[3][idx] + p.lam10[idx] / r10);
+    const float form11 = tmp[n] * wy[j];
+    const float hn = (form1 - r11 * form11 + th * p.gate[5][idx]) / (r10 + th);
+    p.gate[5][idx] = hn;
+    if (p.h_lo) p.h_lo[idx] = tf32_lo(hn);
+  }
+}
+// a (:262-266) and lambda11 (:269-272)
+__global__ void __launch_bounds__(NT) l_last_a_kernel(const float* h, const float* wy, const float* y, float* a, float* lam11,
+                                                      float rho11, float n_norm, float a_den, int64_t n, int64_t ldn, int H) {
+  const int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+  if (i >= n) return;
+  float d = 0.f;
+  for (int j = 0; j < H; ++j) d = fmaf(h[(int64_t)j * ldn + i], wy[j], d);
+  const float l = lam11[i];
+  const float an = (2.0f * y[i] / n_norm + rho11 * d - l) / a_den;
+  a[i] = an;
+  lam11[i] = l + rho11 * (an - d);
+}
+__global__ void __launch_bounds__(NT) l_duals_kernel(const LSlot p) {
+  const int64_t total = (int64_t)p.H * p.ldn;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    if (idx % p.ldn >= p.n) continue;
+    l_duals(p, idx, total, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- host helpers
+unsigned ew_grid(int64_t total) {
+  const int64_t b = (total + NT - 1) / NT;
+  return (unsigned)(b < 148 * 8 ? b : 148 * 8);
+}
+
+int validate_l(const admm_l_problem* lp, const char* who) {
+  if (!lp) { set_error("%s: null problem", who); return ADMM_EINVAL; }
+  int rc = validate(&lp->base, who);
+  if (rc) return rc;
+  ADMM_REQUIRE(lp->base.O == 1, "%s: ADMM-LSTM-L has a single output (W_y is [H,1], main.py:83)", who);
+  for (int g = 0; g < 4; ++g)
+    ADMM_REQUIRE(lp->z[g] && lp->lam_s[g] && lp->lam_p[g], "%s: null z / lambda buffers", who);
+  ADMM_REQUIRE(lp->lam9 && lp->lam10 && lp->base.a && lp->base.dual_y, "%s: null lambda9 / lambda10 / a / lambda11", who);
+  return ADMM_OK;
+}
+
+LSlot make_slot(const admm_l_problem* lp, int s, const float* P) {
+  LSlot k;
+  const admm_problem& b = lp->base;
+  const int64_t slab = (int64_t)b.H * b.ldn;
+  k.n = b.n; k.ldn = b.ldn; k.H = b.H;
+  for (int q = 0; q < 6; ++q) k.gate[q] = b.gate[q] + (int64_t)s * slab;
+  k.c_prev = b.gate[4] + (int64_t)(s - 1) * slab;
+  for (int q = 0; q < 4; ++q) {
+    k.z[q] = lp->z[q] + (int64_t)s * slab;
+    k.lam_s[q] = lp->lam_s[q] + (int64_t)s * slab;
+    k.lam_p[q] = lp->lam_p[q] + (int64_t)s * slab;
+  }
+  k.lam9 = lp->lam9 + (int64_t)s * slab;
+  k.lam10 = lp->lam10 + (int64_t)s * slab;
+  k.P = P;
+  k.h_lo = (b.tc_ws && tc_eligible(&b)) ? tc_h_lo(&b) + (int64_t)s * slab : nullptr;
+  k.hp = lp->hp;
+  return k;
+}
+
+int gemm_P(const admm_l_problem* lp, int s, float* scratch, cudaStream_t st) {
+  GateGemmArgs a = base_args(&lp->base, s);
+  a.scratch = scratch; a.tc = 1;
+  return run_gate_gemm(GG_RAWZ, &lp->base, a, 1, st);
+}
+
+}  // namespace
+}  // namespace admm
+
+using namespace admm;
+
+extern "C" {
+
+int admm_l_sizeof_problem(void) { return (int)sizeof(admm_l_problem); }
+
+int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, void* stream) {
+  int rc = validate_l(lp, "admm_l_forward_t");
+  if (rc) return rc;
+  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch, "admm_l_forward_t: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = gemm_P(lp, s, scratch, st))) return rc;
+  const LSlot k = make_slot(lp, s, scratch);
+  l_forward_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k);
+  count_launch();
+  return check_launch("l_forward");
+}
+
+int admm_l_output(const admm_l_problem* lp, void* stream) {
+  int rc = validate_l(lp, "admm_l_output");
+  if (rc) return rc;
+  const admm_problem& b = lp->base;
+  return launch_output(b.gate[5] + (int64_t)b.T * b.H * b.ldn, b.wy, b.a, b.ldn, b.H, 1, (cudaStream_t)stream);
+}
+
+int admm_l_sums(const admm_l_problem* lp, int t0, int tc, float* scratch, double* acc_x, double* acc_h, void* stream) {
+  int rc = validate_l(lp, "admm_l_sums");
+  if (rc) return rc;
+  const admm_problem& b = lp->base;
+  ADMM_REQUIRE(t0 >= 0 && tc >= 1 && t0 + tc <= b.T, "admm_l_sums: bad timestep range %d+%d", t0, tc);
+  ADMM_REQUIRE(scratch && acc_x && acc_h, "admm_l_sums: null buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t half = 5LL * b.H * tc * b.ldn;
+  LPack k;
+  k.n = b.n; k.ldn = b.ldn; k.H = b.H; k.tc = tc; k.t0 = t0;
+  for (int g = 0; g < 4; ++g) { k.z[g] = lp->z[g]; k.lam_s[g] = lp->lam_s[g]; }
+  k.h = b.gate[5]; k.rho_s = lp->hp.rho_s; k.r = scratch; k.r_lo = scratch + half;
+  l_pack_kernel<<<ew_grid((int64_t)b.H * b.ldn * tc), NT, 0, st>>>(k);
+  count_launch();
+  if ((rc = check_launch("l_pack"))) return rc;
+  const bool use_tc = b.tc_ws && tc_eligible(&b);
+  AtrArgs r;
+  memset(&r, 0, sizeof(r));
+  r.ldn = b.ldn; r.H = b.H; r.tc = tc; r.rows = 5 * b.H; r.rpg = b.H;
+  r.scratch = scratch; r.scratch_lo = use_tc ? scratch + half : nullptr;
+  // src = x: P_x[g] and S_xh
+  r.K = b.D; r.a_src = b.x + (int64_t)t0 * b.D * b.ldn; r.a_tstride = (int64_t)b.D * b.ldn; r.g_acc = acc_x;
+  rc = use_tc ? atr_tc(&b, r, st) : atr_simt(r, st);
+  if (rc) return rc;
+  // src = h_{t-1}: P_h[g] and S_hh
+  r.K = b.H; r.a_src = b.gate[5] + (int64_t)t0 * b.H * b.ldn; r.a_tstride = (int64_t)b.H * b.ldn; r.g_acc = acc_h;
+  return use_tc ? atr_tc(&b, r, st) : atr_simt(r, st);
+}
+
+int admm_l_gram_xx(const admm_l_problem* lp, double* sxx, void* stream) {
+  int rc = validate_l(lp, "admm_l_gram_xx");
+  if (rc) return rc;
+  const admm_problem& b = lp->base;
+  ADMM_REQUIRE(sxx, "admm_l_gram_xx: null buffer");
+  // x is [T][D][ldn]: as R it has D rows per timestep, i.e. T launches with tc = 1 (done once per run)
+  for (int t = 0; t < b.T; ++t) {
+    AtrArgs r;
+    memset(&r, 0, sizeof(r));
+    r.ldn = b.ldn; r.H = b.H; r.tc = 1; r.rows = b.D; r.rpg = b.D;
+    r.K = b.D; r.a_src = b.x + (int64_t)t * b.D * b.ldn; r.a_tstride = (int64_t)b.D * b.ldn;
+    r.scratch = r.a_src; r.scratch_lo = nullptr; r.g_acc = sxx;
+    if ((rc = atr_simt(r, (cudaStream_t)stream))) return rc;
+  }
+  return ADMM_OK;
+}
+
+int admm_l_sums_last(const admm_l_problem* lp, double* s_tt, double* p_t, void* stream) {
+  int rc = validate_l(lp, "admm_l_sums_last");
+  if (rc) return rc;
+  const admm_problem& b = lp->base;
+  ADMM_REQUIRE(s_tt && p_t, "admm_l_sums_last: null buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t slab = (int64_t)b.H * b.ldn;
+  const bool use_tc = b.tc_ws && tc_eligible(&b);
+  AtrArgs r;
+  memset(&r, 0, sizeof(r));
+  r.ldn = b.ldn; r.H = b.H; r.tc = 1; r.rows = b.H; r.rpg = b.H;
+  r.K = b.H; r.a_src = b.gate[5] + (int64_t)b.T * slab; r.a_tstride = slab;
+  r.scratch = r.a_src; r.scratch_lo = use_tc ? tc_h_lo(&b) + (int64_t)b.T * slab : nullptr;
+  r.g_acc = s_tt;
+  rc = use_tc ? atr_tc(&b, r, st) : atr_simt(r, st);
+  if (rc) return rc;
+  l_pt_kernel<<<b.H, NT, 0, st>>>(b.gate[5] + (int64_t)b.T * slab, b.a, b.dual_y, lp->hp.rho11, b.n, b.ldn, p_t);
+  count_launch();
+  return check_launch("l_pt");
+}
+
+int admm_l_sweep_max(const admm_l_problem* lp, int s, float* scratch, float* red_max, void* stream) {
+  int rc = validate_l(lp, "admm_l_sweep_max");
+  if (rc) return rc;
+  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max, "admm_l_sweep_max: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = gemm_P(lp, s, scratch, st))) return rc;
+  const LSlot k = make_slot(lp, s, scratch);
+  l_max_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k, red_max);
+  count_launch();
+  return check_launch("l_max");
+}
+
+int admm_l_sweep_gates(const admm_l_problem* lp, int s, const float* scratch, float* red_max, double* red_sum, void* stream) {
+  int rc = validate_l(lp, "admm_l_sweep_gates");
+  if (rc) return rc;
+  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum, "admm_l_sweep_gates: bad arguments");
+  const LSlot k = make_slot(lp, s, scratch);
+  l_gates_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
+  count_launch();
+  return check_launch("l_gates");
+}
+
+int admm_l_sweep_cell(const admm_l_problem* lp, int s, const float* scratch, const float* red_max, const double* red_sum,
+                      void* stream) {
+  int rc = validate_l(lp, "admm_l_sweep_cell");
+  if (rc) return rc;
+  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum, "admm_l_sweep_cell: bad arguments");
+  const LSlot k = make_slot(lp, s, scratch);
+  const unsigned grid = ew_grid((int64_t)k.H * k.ldn);
+  if (s == lp->base.T) l_cell_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
+  else l_cell_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
+  count_launch();
+  return check_launch("l_cell");
+}
+
+int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, const float* scratch, void* stream) {
+  int rc = validate_l(lp, "admm_l_last");
+  if (rc) return rc;
+  ADMM_REQUIRE(theta_h && tmp && scratch, "admm_l_last: null buffers");
+  const admm_problem& b = lp->base;
+  cudaStream_t st = (cudaStream_t)stream;
+  const LSlot k = make_slot(lp, b.T, scratch);
+  const unsigned nb = (unsigned)((b.n + NT - 1) / NT);
+  const unsigned grid = ew_grid((int64_t)k.H * k.ldn);
+  l_form10_kernel<<<nb, NT, 0, st>>>(k.gate[5], b.wy, b.a, b.dual_y, lp->hp.rho11, b.n, b.ldn, b.H, tmp);
+  l_last_h_kernel<<<grid, NT, 0, st>>>(k, b.wy, tmp, theta_h);
+  const float a_den = (float)(2.0 / (double)lp->hp.n_norm + (double)lp->hp.rho11);
+  l_last_a_kernel<<<nb, NT, 0, st>>>(k.gate[5], b.wy, b.y, b.a, b.dual_y, lp->hp.rho11, lp->hp.n_norm, a_den, b.n, b.ldn, b.H);
+  l_duals_kernel<<<grid, NT, 0, st>>>(k);
+  count_launch(4);
+  return check_launch("l_last");
+}
+
+}  // extern "C"

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(NT) atr_simt_kernel(const AtrArgs p, int chunk
   const int tid = threadIdx.x;
   const int tk = tid / TCC, tcx = tid % TCC;
   const int k0 = blockIdx.x * KT, c0 = blockIdx.y * CT;
-  const int K = p.K, C = 4 * p.H;
+  const int K = p.K, C = p.rows ? p.rows : 4 * p.H;
+  const int rpg = p.rpg ? p.rpg : p.H;
   const int64_t ldn = p.ldn;
   const int chunks_per_t = (int)(ldn / BR);
   const int ch_begin = blockIdx.z * chunks_per_cta;
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(NT) atr_simt_kernel(const AtrArgs p, int chunk
     for (int b = 0; b < MC; ++b) {
       const int c = c0 + (b / 4) * (CT / VC) + tcx * 4 + (b % 4);
       if (c >= C) continue;
-      const int g = c / p.H, j = c % p.H;
-      atomicAdd(p.g_acc + ((int64_t)g * K + k) * p.H + j, (double)acc[a][b]);
+      const int g = c / rpg, j = c % rpg;
+      atomicAdd(p.g_acc + ((int64_t)g * K + k) * rpg + j, (double)acc[a][b]);
     }
   }
 }
@@ -133,12 +134,13 @@ __global__ void __launch_bounds__(NT) atr_simt_kernel(const AtrArgs p, int chunk
 template <int KT, int CT, int MK, int MC>
 int launch(const AtrArgs& a, cudaStream_t st) {
   const int n_chunks = (int)(a.tc * (a.ldn / BR));
-  const int tiles = ((a.K + KT - 1) / KT) * ((4 * a.H + CT - 1) / CT);
+  const int rows = a.rows ? a.rows : 4 * a.H;
+  const int tiles = ((a.K + KT - 1) / KT) * ((rows + CT - 1) / CT);
   int splits = (2 * 148 + tiles - 1) / tiles;
   splits = max(1, min(splits, n_chunks));
   const int cpc = (n_chunks + splits - 1) / splits;
   splits = (n_chunks + cpc - 1) / cpc;
-  dim3 grid((a.K + KT - 1) / KT, (4 * a.H + CT - 1) / CT, splits);
+  dim3 grid((a.K + KT - 1) / KT, (rows + CT - 1) / CT, splits);
   atr_simt_kernel<KT, CT, MK, MC><<<grid, NT, 0, st>>>(a, cpc, n_chunks);
   count_launch();
   return check_launch("atr_simt");

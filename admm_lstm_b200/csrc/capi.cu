@@ -49,7 +49,7 @@ static int device_ok() {
   return cached = (prop.major == 10) ? n : 0;
 }
 
-static int validate(const admm_problem* p, const char* who) {
+int validate(const admm_problem* p, const char* who) {
   if (!p) { set_error("%s: null problem", who); return ADMM_EINVAL; }
   if (!device_ok()) { set_error("%s: no sm_100 CUDA device (this library has no CPU path)", who); return ADMM_ENODEV; }
   ADMM_REQUIRE(p->n > 0 && p->n_global >= p->n, "%s: bad n=%lld n_global=%lld", who, (long long)p->n, (long long)p->n_global);
@@ -61,7 +61,7 @@ static int validate(const admm_problem* p, const char* who) {
   return ADMM_OK;
 }
 
-static GateGemmArgs base_args(const admm_problem* p, int t_first) {
+GateGemmArgs base_args(const admm_problem* p, int t_first) {
   // t_first = first timestep t (1-based) of the launch
   GateGemmArgs a;
   memset(&a, 0, sizeof(a));
@@ -82,7 +82,7 @@ static GateGemmArgs base_args(const admm_problem* p, int t_first) {
   return a;
 }
 
-static int run_gate_gemm(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st) {
+int run_gate_gemm(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st) {
   if (p->tc_ws && tc_eligible(p)) return gate_gemm_tc(mode, p, a, tc, st);
   return gate_gemm_simt(mode, a, tc, st);
 }
@@ -196,6 +196,7 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   }
   if (rc) return rc;
   AtrArgs r;
+  memset(&r, 0, sizeof(r));
   r.ldn = p->ldn; r.H = p->H; r.tc = tc;
   r.scratch_lo = a.scratch_q;
   r.K = (src == ADMM_SRC_X) ? p->D : p->H;

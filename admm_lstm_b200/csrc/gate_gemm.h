@@ -52,6 +52,9 @@ struct AtrArgs {
   const float* scratch;     // R^T
   const float* scratch_lo;  // tf32 low part of R^T (tensor-core path) or nullptr
   double* g_acc;
+  // Generalisation used by the Gram / right-hand-side sums of ADMM-LSTM-L: R has `rows` rows (0 = the default 4*H)
+  // in groups of `rpg` (0 = H): G_acc[c / rpg][k][c % rpg] += sum A_src[k][n] R[c][n].
+  int32_t rows, rpg;
 };
 int atr_simt(const AtrArgs& a, cudaStream_t st);
 

@@ -885,7 +885,7 @@ __host__ __device__ constexpr uint32_t make_idesc_kmajor(int m, int n) {
 template <int NT_>
 __global__ void __launch_bounds__(ATR_THREADS, 1)
 atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H, int tc, int64_t ldn, int slab0,
-              int chunks_per_cta, int n_chunks, int use_atomics) {
+              int chunks_per_cta, int n_chunks, int use_atomics) {   // H = rows per group of R (AtrArgs::rpg)
   constexpr int A_BYTES = 128 * ATR_BKN * 4;        // R tile   16 KB
   constexpr int B_BYTES = NT_ * ATR_BKN * 4;        // h tile   NT x 128 B
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -1001,9 +1001,11 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
   }
   AtrMaps m;
   const uint64_t ldn = a.ldn, H = a.H, tc = a.tc, T1 = p->T + 1;
+  const uint64_t rows = a.rows ? a.rows : 4 * H;
+  const int rpg = a.rpg ? a.rpg : a.H;
   int rc = 0;
-  rc |= make_map_box(&m.r, a.scratch, ldn, tc, 4 * H, ldn, tc * ldn, ATR_BKN, 1, 128);
-  rc |= make_map_box(&m.r_lo, a.scratch_lo, ldn, tc, 4 * H, ldn, tc * ldn, ATR_BKN, 1, 128);
+  rc |= make_map_box(&m.r, a.scratch, ldn, tc, rows, ldn, tc * ldn, ATR_BKN, 1, 128);
+  rc |= make_map_box(&m.r_lo, a.scratch_lo, ldn, tc, rows, ldn, tc * ldn, ATR_BKN, 1, 128);
   if (src_is_x) {     // A_src = x: [T][D][ldn]; rows k >= D are zero-filled by TMA and masked in the epilogue
     const uint64_t D = p->D;
     rc |= make_map_box(&m.h, p->x, ldn, D, p->T, ldn, D * ldn, ATR_BKN, NT_, 1);
@@ -1014,14 +1016,14 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
   }
   if (rc) return ADMM_ECUDA;
   const int n_chunks = (int)(tc * (ldn / ATR_BKN));
-  const int tiles = (int)((4 * H / 128) * ((a.K + NT_ - 1) / NT_));
+  const int tiles = (int)((rows / 128) * ((a.K + NT_ - 1) / NT_));
   int splits = (148 + tiles - 1) / tiles;
   if (tiles * splits > 148 && splits > 1) --splits;          // stay within one wave of 148 single-CTA SMs
   splits = max(1, min(splits, n_chunks));
   const int cpc = (n_chunks + splits - 1) / splits;
   splits = (n_chunks + cpc - 1) / cpc;
-  dim3 grid((unsigned)(4 * H / 128), (unsigned)((a.K + NT_ - 1) / NT_), (unsigned)splits);
-  atr_tc_kernel<NT_><<<grid, ATR_THREADS, SMEM, st>>>(m, a.g_acc, a.K, a.H, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1);
+  dim3 grid((unsigned)(rows / 128), (unsigned)((a.K + NT_ - 1) / NT_), (unsigned)splits);
+  atr_tc_kernel<NT_><<<grid, ATR_THREADS, SMEM, st>>>(m, a.g_acc, a.K, rpg, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1);
   count_launch();
   return check_launch("atr_tc");
 }
@@ -1030,7 +1032,7 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
 
 // Tensor-core G += A_src^T R.  `a.a_src` must be a slab of p->gate[5] (src = h, K = H) or of p->x (src = x, K = D).
 int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st) {
-  if (!a.scratch_lo) return atr_simt(a, st);
+  if (!a.scratch_lo || ((a.rows ? a.rows : 4 * a.H) % 128) != 0) return atr_simt(a, st);
   const bool src_is_x = (a.a_src >= p->x && a.a_src < p->x + (int64_t)p->T * p->D * p->ldn);
   if (src_is_x) {
     if (p->D < 8) return atr_simt(a, st);               // a handful of rows: not worth a 64-row MMA tile

@@ -16,4 +16,9 @@ int tc_refresh_wx_delta(const admm_problem* p, cudaStream_t st);
 int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st);
 int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st);
 float* tc_h_lo(const admm_problem* p);
+
+// capi.cu helpers shared with admm_l.cu
+int validate(const admm_problem* p, const char* who);
+GateGemmArgs base_args(const admm_problem* p, int t_first);
+int run_gate_gemm(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st);
 }  // namespace admm

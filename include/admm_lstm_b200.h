@@ -199,6 +199,71 @@ int admm_debug_preact(const admm_problem* p, int t, float* out, int use_tc, void
  * (bench.py reports it as gpu_launches). */
 int64_t admm_launch_count(int reset);
 
+/* ================================================================================================================
+ * ADMM-LSTM-L: the linearised ADMM of
+ * /root/reference/comparison_experiment/admm_l/admm_lstm.py driven by admm_l/main.py:139-191.
+ *
+ * Layout as above (feature-major, sample fastest).  The reference's per-timestep dictionaries z*[t], f[t] ... h[t],
+ * t = 0..T-1, live in slot t+1 of [T+1][H][ldn] tensors; slot 0 is the all-zero h[-1] / c[-1] (main.py:87-88).
+ * `base` carries x, y ([1][ldn]; the reference's W_y is [H,1], main.py:83), gate[] = i,f,g,o,c,h, the stacked weights
+ * wx [4][D][H] / wh [4][H][H] in the order i,f,g,o, wy [H], a ([1][ldn]) and dual_y = lambda11 ([1][ldn]);
+ * base.dual[] / base.dual_h / base.hp are unused.  Rows n >= base.n (ghost samples) are never touched and stay zero.
+ * ================================================================================================================ */
+typedef struct admm_l_hyper {
+  float rho_s;    /* RHO_singular: rho1,3,5,7  (main.py:115)      */
+  float rho_p;    /* RHO_plural:   rho2,4,6,8  (main.py:120)      */
+  float rho9, rho10, rho11;                 /* main.py:125-129     */
+  float lam_w, lam_u, lam_y;                /* lambda00, lambda02, lambda03 (main.py:112-114) */
+  float n_norm;   /* the constant 4224 of update_a (admm_lstm.py:263-264) */
+} admm_l_hyper;
+
+typedef struct admm_l_problem {
+  admm_problem base;
+  float* z[4];      /* z_i z_f z_g z_o           : each [T+1][H][ldn] */
+  float* lam_s[4];  /* lambda3, 1, 7, 5 (i f g o): z  = x W + h U     */
+  float* lam_p[4];  /* lambda4, 2, 8, 6 (i f g o): gate = act(z)      */
+  float* lam9;      /* c_t = f c_{t-1} + i g                          */
+  float* lam10;     /* h_t = o tanh(c_t)                              */
+  admm_l_hyper hp;
+} admm_l_problem;
+
+int admm_l_sizeof_problem(void);
+
+/* main.py:85-103 at slot s = 1..T: z, gates, c, h (and the tensor-core side buffer of h).  scratch: 4*H*ldn floats. */
+int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, void* stream);
+/* a = h_T W_y (main.py:102) */
+int admm_l_output(const admm_l_problem* lp, void* stream);
+
+/* Gram and right-hand-side sums of the weight subproblems (admm_lstm.py:107-163).  The residual
+ * -z_t + x_t W + h_{t-1} U - lambda_t/rho is linear in W and U, so with V_g = z_g + lambda_g/rho
+ *      acc_x[g] += sum_t x_t^T V_g,t  (g = 0..3, [D][H]),   acc_x[4] += sum_t x_t^T h_{t-1}   = S_xh
+ *      acc_h[g] += sum_t h_{t-1}^T V_g,t      ([H][H]),      acc_h[4] += sum_t h_{t-1}^T h_{t-1} = S_hh
+ * every gradient and every backtracking probe of the eight updates is O(K^2 H) algebra on these sums; they are what is
+ * all-reduced across sample shards.  One call handles the timesteps [t0, t0+tc) (0-based, reference numbering);
+ * scratch: 10*H*tc*ldn floats (V and h rows and their tf32 low parts).  gram_xx: sxx[D][D] += sum_t x_t^T x_t (constant
+ * over the run).  sums_last: s_tt[H][H] += h_T^T h_T, p_t[H] += h_T^T (a + lambda11/rho11)  (update_Wy, :76-104). */
+int admm_l_sums(const admm_l_problem* lp, int t0, int tc, float* scratch, double* acc_x, double* acc_h, void* stream);
+int admm_l_gram_xx(const admm_l_problem* lp, double* sxx, void* stream);
+int admm_l_sums_last(const admm_l_problem* lp, double* s_tt, double* p_t, void* stream);
+
+/* The sweep at slot s (main.py:149-188) in three launches separated by the algorithm's own global reductions:
+ *  max   : P = x W + h_{s-1} U for the four gates (gate GEMM -> scratch, 4*H*ldn floats) and
+ *          red_max[g] = max |gate_g - lambda_p,g / rho_p|  (update_z/update_zg, :168,:179), g = i,f,g,o
+ *  gates : z_f,f, z_i,i, z_o,o, z_g,g in the reference's Gauss-Seidel order (:166-220);
+ *          red_max[4] = max |(h - lambda10/rho10)/o|, red_sum[0] = sum o^2  (update_c, :225,:230)
+ *  cell  : c (:223-241), h for s < T (:249-250) and the ten dual updates (:274-311); for s == T only c is written and
+ *          admm_l_last() finishes the timestep.
+ * red_max: 8 floats (non-negative, combined with MAX across shards), red_sum: 1 double (SUM); both zeroed by the
+ * caller before `max`. */
+int admm_l_sweep_max(const admm_l_problem* lp, int s, float* scratch, float* red_max, void* stream);
+int admm_l_sweep_gates(const admm_l_problem* lp, int s, const float* scratch, float* red_max, double* red_sum, void* stream);
+int admm_l_sweep_cell(const admm_l_problem* lp, int s, const float* scratch, const float* red_max, const double* red_sum,
+                      void* stream);
+/* s == T: h_T with theta_h[0] (update_h :251-258; the loop's exit is theta = smallest power of two >= max(1,
+ * rho11 ||W_y||^2)), a (:262-266), lambda11 (:269-272), then the duals of slot T.  tmp: ldn floats;
+ * scratch still holds P of slot T. */
+int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, const float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,7 @@ class ADMMLOptimizer(object):
         if self._lib.admm_device_ok() <= 0:
             raise _lib.AdmmLibraryError("no sm_100 (B200) device visible to libadmm_lstm_b200.so")
         self.comm = comm if comm is not None else Comm()
+        self.kernel_events = None
         assert train_x.dim() == 3 and train_y.dim() == 2 and train_y.size(1) == 1, "train_x [N,T,D], train_y [N,1]"
         self.batch_size, self.seq_len, self.input_size = (int(v) for v in train_x.shape)
         self.hidden_size = int(weights["Wy"].shape[0])
@@ -163,9 +164,42 @@ class ADMMLOptimizer(object):
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _call(self, name, *args) -> None:
-        rc = getattr(self._lib, name)(*args)
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(self._lib, name)(*args)
+            e1.record()
+            self.kernel_events.append((name, e0, e1))
+        else:
+            rc = getattr(self._lib, name)(*args)
         if rc != 0:
             _lib.check(rc, name)
+
+    def enable_kernel_timing(self, enabled: bool = True) -> None:
+        """Bracket every C-ABI call with CUDA events on the launching stream (bench.py roofline)."""
+        self.kernel_events = [] if enabled else None
+
+    def kernel_time_summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.kernel_events or []:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1))
+        return out
+
+    def refresh_inputs(self, train_x: torch.Tensor, train_y: torch.Tensor) -> None:
+        """Re-upload this rank's samples from (pinned) host memory -- the host->device leg of bench.py's end-to-end
+        measurement; S_xx is recomputed from the new inputs."""
+        n = self.n_local
+        self._x[:, :, :n].copy_(train_x.to(self.device, non_blocking=True).permute(1, 2, 0))
+        self._y[:, :n].copy_(train_y.to(self.device, non_blocking=True).t())
+        st = _stream_ptr()
+        if self._tc_ws is not None:
+            self._call("admm_tc_refresh", self._bp, _lib.TC_INPUTS, st)
+        sxx = torch.zeros_like(self._sxx)
+        self._call("admm_l_gram_xx", self._lpp, sxx.data_ptr(), st)
+        self.comm.allreduce_sum_(sxx)
+        self._sxx = 0.5 * (sxx + sxx.t())
 
     def _time_chunks(self):
         T, tc = self.seq_len, self._tc_chunk

@@ -506,6 +506,67 @@ class ADMMBasedOptimizer(object):
         self._call("admm_last_select", self._pp, self._acc_last.data_ptr(), self._theta_h.data_ptr(), st)
         self._call("admm_last_apply", self._pp, self._theta_h.data_ptr(), self._metrics.data_ptr(), st)
 
+    # ------------------------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self) -> Dict[str, object]:
+        """This rank's ADMM state (absent upstream): gates i,f,g,o,c,h and a, duals, in the reference's
+        shapes on the CPU, plus what a resumed run needs to continue bit-identically (hyper-parameters, variant, the
+        theta history that sizes the probe windows).  The weights are NOT included: they live in the model, whose file
+        format (torch.save(model), demo.py:302-308) is unchanged."""
+        out: Dict[str, object] = {
+            "format": 1, "variant": self.variant, "with_dual_y": self.with_dual_y,
+            "shape": (self.n_local, self.seq_len, self.input_size, self.hidden_size, self.output_size),
+            "n_global": self.n_global, "rank": self.comm.rank, "world_size": self.comm.world_size,
+            "rho": {k: float(v) for k, v in self.rhos.items()}, "beta": {k: float(v) for k, v in self.betas.items()},
+            "step_index": self._step_index,
+            "theta_w": self._theta_w.cpu(), "theta_h": self._theta_h.cpu(),
+            "gates": {k: self.gates[k].cpu().contiguous() for k in _STATE_KEYS + ("a",)},
+            "duals": {k: self.duals[k].cpu().contiguous() for k in ("i", "f", "g", "o", "c", "y")},
+            "dual_h_T": self._dual_h.t()[: self.n_local].cpu().contiguous(),
+        }
+        return out
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        log_assert(sd.get("format") == 1, "Unknown optimizer state format.")
+        log_assert(tuple(sd["shape"]) == (self.n_local, self.seq_len, self.input_size, self.hidden_size, self.output_size),
+                   f"Optimizer state shape mismatch (Got: {tuple(sd['shape'])}).")
+        log_assert(sd["variant"] == self.variant and bool(sd["with_dual_y"]) == self.with_dual_y,
+                   "Optimizer state was written by another variant.")
+        n, dev = self.n_local, self.device
+        for k in _STATE_KEYS:
+            self._state[k][:, :, :n] = sd["gates"][k].to(dev).permute(1, 2, 0)
+        for k in ("i", "f", "g", "o", "c"):
+            self._dual[k][:, :, :n] = sd["duals"][k].to(dev).permute(1, 2, 0)
+        self._dual_h[:, :n] = sd["dual_h_T"].to(dev).t()
+        self._a[:, :n] = sd["gates"]["a"].to(dev).t()
+        self._dual_y[:, :n] = sd["duals"]["y"].to(dev).t()
+        self._theta_w.copy_(sd["theta_w"])
+        self._theta_h.copy_(sd["theta_h"])
+        # the probe-window hint of the next two steps comes from the saved thetas (the ring is empty after a restart)
+        self._step_index = int(sd["step_index"])
+        for slot in self._theta_ring:
+            slot[1], slot[2] = None, -1
+        for back in (1, 2):
+            idx = self._step_index - back
+            if idx >= 0:
+                slot = self._theta_ring[idx % len(self._theta_ring)]
+                slot[0][:8].copy_(sd["theta_w"])
+                slot[0][8:].copy_(sd["theta_h"])
+                slot[1] = torch.cuda.Event()
+                slot[1].record()
+                slot[2] = idx
+        self._resync_weights_if_replaced()
+        self.state_changed()
+
+    def save_state(self, path: str) -> str:
+        """Write this rank's shard next to the model file: `<path>.rank<r>of<w>.pt`."""
+        fn = f"{path}.rank{self.comm.rank}of{self.comm.world_size}.pt"
+        torch.save(self.state_dict(), fn)
+        return fn
+
+    def load_state(self, path: str) -> None:
+        fn = f"{path}.rank{self.comm.rank}of{self.comm.world_size}.pt"
+        self.load_state_dict(torch.load(fn, map_location="cpu", weights_only=False))
+
     # ------------------------------------------------------------------------------------ observables
     def metrics(self) -> Dict[str, float]:
         """Objective / primal / dual residuals of the step just taken (the reference

@@ -102,6 +102,143 @@ def time_oracle(workload, steps, warmup, threads=None):
                       f"{steps} step(s) after {warmup} warm-up, {dt:.2f} s/step"}, dt
 
 
+def make_l_weights(d, h, seed=12345):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    w = {"Wy": (rng.standard_normal((h, 1)) * 0.1).astype(np.float32)}
+    for g in "fiog":
+        w["W" + g] = (rng.standard_normal((d, h)) * 0.1).astype(np.float32)
+        w["U" + g] = (rng.standard_normal((h, h)) * 0.1).astype(np.float32)
+    return w
+
+
+def time_oracle_l(workload, steps, warmup):
+    """CPU arm of ADMM-LSTM-L: oracle/admm_l_oracle.py on a bounded sample."""
+    from oracle.admm_l_oracle import OracleADMML
+    n_gpu, t, d, h, o, pname, cpu_n, cls = WORKLOADS[workload]
+    x, y, _ = make_data(cpu_n, t, d, h, 1, 0, False)
+    w = make_l_weights(d, h)
+    ora = OracleADMML({g: w["W" + g] for g in "fiog"}, {g: w["U" + g] for g in "fiog"}, w["Wy"], x, y)
+    for _ in range(warmup):
+        ora.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ora.step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    cores = os.cpu_count() or 1
+    return {"value": cpu_n * t / dt, "unit": "sample-timestep updates/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/admm_l_oracle.py (numpy fp32 + OpenBLAS, {cores} threads), same T/D/H, N={cpu_n} samples, "
+                      f"{steps} step(s) after {warmup} warm-up, {dt:.2f} s/step"}, dt
+
+
+def bench_admm_l(args, rank, world, local_rank, config, metric, unit):
+    """ADMM-LSTM-L arm: same contract as the main arm; the roofline object is the Gram / right-hand-side
+    pass (admm_l_sums: packing kernel + two runs of the tcgen05 A^T R reduction GEMM)."""
+    import torch
+    import torch.distributed as dist
+    from admm_lstm_b200 import _lib
+    from admm_lstm_b200.admm_l import ADMMLOptimizer
+    n_gpu, T, D, H, O, pname, cpu_n, cls = WORKLOADS[args.workload]
+    n_gpu = args.n_per_gpu or n_gpu // 2            # 20 state tensors instead of 11 (+ zstore): half the samples fit
+    config.update({"samples_per_gpu": n_gpu, "O": 1, "hyper_parameters": "admm_l/main.py:111-129 as shipped"})
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    x, y, _ = make_data(n_gpu, T, D, H, 1, 1000 + rank, False)
+    w = {k: torch.from_numpy(v) for k, v in make_l_weights(D, H).items()}
+    x_pin, y_pin = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    opt = ADMMLOptimizer(w, x_pin, y_pin, sharding="presharded", n_norm=float(n_gpu * max(world, 1)),
+                         use_tensor_cores=(False if args.no_tc else None))
+    del x, y
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        opt.step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib.admm_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        opt.step()
+    e1.record()
+    barrier()
+    launches = int(lib.admm_launch_count(0))
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    opt.enable_kernel_timing(True)
+    for _ in range(2):
+        opt.step()
+    barrier()
+    ksum = opt.kernel_time_summary()
+    opt.enable_kernel_timing(False)
+    pinned = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in (("wx", opt._wx), ("wh", opt._wh), ("wy", opt._wy))}
+    h2d = x_pin.numel() * 4 + y_pin.numel() * 4
+    d2h = sum(v.numel() * 4 for v in pinned.values())
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        opt.refresh_inputs(x_pin, y_pin)
+        opt.step()
+        pinned["wx"].copy_(opt._wx, non_blocking=True)
+        pinned["wh"].copy_(opt._wh, non_blocking=True)
+        pinned["wy"].copy_(opt._wy, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3) / args.steps)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    if rank == 0:
+        peaks = load_peaks()
+        n_total = opt.n_global
+        roofline = None
+        if "admm_l_sums" in ksum:
+            calls, tot_ms = ksum["admm_l_sums"]
+            per_step_ms = tot_ms / 2
+            flops = 2.0 * 5 * H * (D + H) * opt.n_local * T            # useful flops of the two A^T R GEMMs per iteration
+            ach = flops / (per_step_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "frac_of_3xtf32_ceiling": ach / (peaks["bf16_tflops_sustained"] / 6.0),
+                        "kernel": "atr_tc_kernel (Gram / right-hand-side sums) via admm_l_sums, packing kernel included",
+                        "ms_per_step": per_step_ms, "calls_per_step": calls // 2, "share_of_step": per_step_ms / ms_step,
+                        "peak_source": peaks["source"], "algorithmic_per_step": {"flops": flops},
+                        "note": "useful fp32-equivalent flops (2*5H*(D+H) per sample-timestep) against the measured dense "
+                                "bf16 peak; 3xTF32 ceiling = peak/6"}
+        line = {"metric": metric, "value": n_total * T / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "e2e": {"value": n_total * T / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "tensor_cores": bool(opt.uses_tensor_cores),
+                "kernel_ms_per_step": {k: round(v[1] / 2, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},
+                "thetas": {k: float(v) for k, v in opt.thetas.items()}}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = time_oracle_l(args.workload, 1, 0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -166,7 +303,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("ADMM_BENCH_WORKLOAD", "cfg3"), choices=list(WORKLOADS))
-    ap.add_argument("--variant", default="admm", choices=["admm", "no_dual_y"])
+    ap.add_argument("--variant", default="admm", choices=["admm", "no_dual_y", "admm_l"],
+                    help="admm / no_dual_y: the reference's admm.py / admm.no_dual_y.py; admm_l: ADMM-LSTM-L (admm_l/main.py)")
     ap.add_argument("--n-per-gpu", type=int, default=0, help="override the per-GPU sample count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="force the fp32 CUDA-core path")
@@ -191,7 +329,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        base, dt = time_oracle(args.workload, max(args.steps, 1), min(args.warmup, 1))
+        if args.variant == "admm_l":
+            base, dt = time_oracle_l(args.workload, max(args.steps, 1), min(args.warmup, 1))
+        else:
+            base, dt = time_oracle(args.workload, max(args.steps, 1), min(args.warmup, 1))
         line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": max(args.steps, 1), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -201,6 +342,8 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    if args.variant == "admm_l":
+        return bench_admm_l(args, rank, world, local_rank, config, metric, unit)
     import torch
     import torch.distributed as dist
     from admm_lstm_b200 import _lib

@@ -2,6 +2,8 @@
 the unmodified reference.  Tolerances: weights / gates / a / MSE /
 objective relative <= 1e-4 (scale-relative: max|diff| / max|ref|); duals absolute
 1e-4 * max(max|dual|, rho) (they are cancellation residues); final train/val loss within 1 %."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -454,3 +456,34 @@ def test_stored_preactivations_equal_recomputed():
     for k in ("i", "f", "g", "o", "c", "h"):
         assert torch.equal(a.gates[k], b.gates[k]), k
     assert a.theta_trace() == b.theta_trace()
+
+
+@pytest.mark.parametrize("shape,tc", [((150, 4, 3, 12, 2), False), ((300, 3, 16, 64, 1), True)])
+def test_checkpoint_resume_is_bit_identical(tmp_path, shape, tc):
+    """optimizer state saved next to the model file; a resumed run continues with the same iterates."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    n, t, d, h, o = shape
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=9)
+    model, a = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=tc)
+    for _ in range(3):
+        a.step()
+    torch.save(model, tmp_path / "model.pt")
+    fn = a.save_state(str(tmp_path / "model.pt.admm"))
+    assert os.path.exists(fn)
+    for _ in range(3):
+        a.step()
+    model_b = torch.load(tmp_path / "model.pt", weights_only=False)
+    from admm_lstm_b200.optimizer import ADMMBasedOptimizer
+    b = ADMMBasedOptimizer(model_b, (torch.from_numpy(x), torch.from_numpy(y)), GOOGLE, verbose=False, variant="admm",
+                           use_tensor_cores=tc)
+    b.load_state(str(tmp_path / "model.pt.admm"))
+    for _ in range(3):
+        b.step()
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert np.array_equal(wa[k], wb[k]), k
+    for k in ("i", "f", "g", "o", "c", "h", "a"):
+        assert torch.equal(a.gates[k], b.gates[k]), k
+    for k in ("i", "f", "g", "o", "c", "h", "y"):
+        assert torch.equal(a.duals[k], b.duals[k]), k

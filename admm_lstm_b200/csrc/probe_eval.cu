@@ -27,9 +27,26 @@ constexpr int NCS = ADMM_FK_SLOTS;
 // Residual of one element for one candidate.  The instruction stream is what bounds this kernel (ncu: issue slots
 // 69 % busy, XU pipe 56 %, at 22 instructions per activation before this was flattened), so the sigmoid path is
 // spelled out: FFMA, FMNMX, FMUL, MUFU.EX2, FADD, MUFU.RCP, 2 FFMA (Newton), 2 FADD, FFMA = 11 issue slots.
+// 1/d for d in [1, 2^116] on the FMA pipe only: bit-trick seed (12 % off) + three Newton steps (1.4e-2, 2e-4, 4e-8).
+// Every second candidate uses it instead of MUFU.RCP: the kernel is bound by the XU pipe (2 MUFU = 16 XU cycles per
+// warp-activation against 11 issue slots), so trading one MUFU for five FMA-pipe instructions on half of the
+// candidates balances the two pipes (12 XU cycles against 13.5 issue slots on average).
+__device__ __forceinline__ float rcp_fma(float d) {
+  float r = __uint_as_float(0x7EF311C7u - __float_as_uint(d));
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
 template <bool IS_G>
-__device__ __forceinline__ float probe_term(float z, float lr, float gv) {
-  const float a = IS_G ? FastMath::tanh(z) : FastMath::sigmoid(z);
+__device__ __forceinline__ float probe_term(float z, float lr, float gv, bool fma_rcp) {   // fma_rcp folds after unrolling
+  float a;
+  if (IS_G) {
+    a = FastMath::tanh(z);
+  } else if (fma_rcp) {
+    a = rcp_fma(1.0f + FastMath::ex2(-1.4426950408889634f * fmaxf(z, -80.0f)));
+  } else {
+    a = FastMath::sigmoid(z);
+  }
   return (a - lr) - gv;                 // the reference's association (admm.py:319-323)
 }
 
@@ -47,12 +64,12 @@ __device__ __forceinline__ void accumulate(const float4& z4, const float4& q4, c
     const float lr = rho_pow2 ? lam[e] * inv_rho : __fdiv_rn(lam[e], rho);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      float u = probe_term<IS_G>(fmaf(q[e], inv_theta[k], z[e]), lr, gv[e]);
+      float u = probe_term<IS_G>(fmaf(q[e], inv_theta[k], z[e]), lr, gv[e], (k & 1) != 0);
       if (!FULL) u *= mask[e];
       acc[k] = fmaf(u, u, acc[k]);
     }
     if (WITH_FW) {
-      float u = probe_term<IS_G>(z[e], lr, gv[e]);
+      float u = probe_term<IS_G>(z[e], lr, gv[e], false);
       if (!FULL) u *= mask[e];
       acc[NC] = fmaf(u, u, acc[NC]);
     }

@@ -449,7 +449,9 @@ def main():
         # (two launches + the candidate evaluation).  admm_sweep_t launches exactly ONE kernel per call, so its CUDA-event
         # time is a per-launch kernel time; the other entry points are reported per call in kernel_classes.
         flops_gate = 8.0 * H * (D + H)                      # useful flops per sample-timestep (2*M*N*K, not the 3x of the split)
-        bytes_sweep = (22.0 * H + D) * 4                    # x_t, h_{t-1}, 10 state reads (+c_{t-1}), 11 state writes
+        # x_t, h_{t-1}, 10 state reads (+c_{t-1}), 11 state writes; +4H when the sweep also stores z_t for the next
+        # iteration's x-phase gradient (admm_problem::z_valid)
+        bytes_sweep = ((26.0 if opt.keeps_preactivations else 22.0) * H + D) * 4
         tc_ceiling = peaks["bf16_tflops_sustained"] / 6.0   # tf32 = bf16/2 dense, and three MMAs per product
         roofline = None
         if "admm_sweep_t" in ksum:

@@ -474,6 +474,13 @@ def main():
                              "algorithmic_per_launch": {"flops": flops_gate * opt.n_local, "bytes": bytes_sweep * opt.n_local},
                              "note": "useful fp32-equivalent flops against the measured dense bf16 peak (sustained); the kernel "
                                      "computes an fp32-accurate 3xTF32 product, whose ceiling is peak/6"})
+        if roofline is not None:
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath):
+                for ent in json.load(open(tpath)).get("admm_sweep_t", []):
+                    if (ent["n_local"], ent["H"], ent["D"]) == (opt.n_local, H, D) and opt.uses_tensor_cores:
+                        roofline["traffic"] = ent["dram_bytes_per_launch"]
+                        roofline["traffic_source"] = ent["source"]
         step_flops = 56.0 * H * (D + H) * opt.n_local * T
         line = {
             "metric": metric, "value": n_total * T / (ms_step * 1e-3), "unit": unit, "n_gpus": world,

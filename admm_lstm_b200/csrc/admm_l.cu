@@ -39,8 +39,19 @@ struct LSlot {
   float* lam10;
   const float* P;        // [4][H][ldn] = x W + h_{s-1} U
   float* h_lo;           // tf32 low part of h at slot s, or nullptr
+  __half* h16_hi;        // fp16 pair of h 2^11 at slot s (the gate GEMM's A operand), or nullptr
+  __half* h16_lo;
   admm_l_hyper hp;
 };
+
+__device__ __forceinline__ void l_store_h_side(const LSlot& p, int64_t idx, float h) {
+  if (!p.h_lo) return;
+  p.h_lo[idx] = tf32_lo(h);
+  const float c = fminf(fmaxf(h * 2048.0f, -65504.0f), 65504.0f);       // 2^11 = SCALE_H of gate_gemm_tc.cu
+  const __half hh = __float2half_rn(c);
+  p.h16_hi[idx] = hh;
+  p.h16_lo[idx] = __float2half_rn(c - __half2float(hh));
+}
 
 __device__ __forceinline__ float block_max(float v, float* red) {
 #pragma unroll
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(NT) l_forward_kernel(const LSlot p) {
     const float h = o * tanhf(c);
     p.gate[0][idx] = i; p.gate[1][idx] = f; p.gate[2][idx] = gg; p.gate[3][idx] = o;
     p.gate[4][idx] = c; p.gate[5][idx] = h;
-    if (p.h_lo) p.h_lo[idx] = tf32_lo(h);
+    l_store_h_side(p, idx, h);
   }
 }
 
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* 
       const float hn = (r10 * (tanhf(c) * o + l10 / r10)) / r10;
       p.gate[4][idx] = c;
       p.gate[5][idx] = hn;
-      if (p.h_lo) p.h_lo[idx] = tf32_lo(hn);
+      l_store_h_side(p, idx, hn);
       l_duals_store(p, idx, d, c, hn, c_);
     }
   }
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(NT) l_last_h_kernel(const LSlot p, const float
     const float form11 = tmp[n] * wy[j];
     const float hn = (form1 - r11 * form11 + th * p.gate[5][idx]) / (r10 + th);
     p.gate[5][idx] = hn;
-    if (p.h_lo) p.h_lo[idx] = tf32_lo(hn);
+    l_store_h_side(p, idx, hn);
   }
 }
 // a (:262-266) and lambda11 (:269-272)
@@ -347,7 +358,13 @@ LSlot make_slot(const admm_l_problem* lp, int s, const float* P) {
   k.lam9 = lp->lam9 + (int64_t)s * slab;
   k.lam10 = lp->lam10 + (int64_t)s * slab;
   k.P = P;
-  k.h_lo = (b.tc_ws && tc_eligible(&b)) ? tc_h_lo(&b) + (int64_t)s * slab : nullptr;
+  k.h_lo = nullptr; k.h16_hi = k.h16_lo = nullptr;
+  if (b.tc_ws && tc_eligible(&b)) {
+    k.h_lo = tc_h_lo(&b) + (int64_t)s * slab;
+    tc_h16(&b, &k.h16_hi, &k.h16_lo);
+    k.h16_hi += (int64_t)s * slab;
+    k.h16_lo += (int64_t)s * slab;
+  }
   k.hp = lp->hp;
   return k;
 }

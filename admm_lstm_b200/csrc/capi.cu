@@ -335,8 +335,9 @@ int admm_tc_refresh(const admm_problem* p, int what, void* stream) {
   if (rc) return rc;
   if (!(p->tc_ws && tc_eligible(p))) return ADMM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((what & ADMM_TC_WEIGHTS) && (rc = tc_refresh_weights(p, st))) return rc;
+  // inputs first: the operand scale of x enters the weights' scales (tc_refresh_inputs re-prepares the weights itself)
   if ((what & ADMM_TC_INPUTS) && (rc = tc_refresh_inputs(p, st))) return rc;
+  if ((what & ADMM_TC_WEIGHTS) && !(what & ADMM_TC_INPUTS) && (rc = tc_refresh_weights(p, st))) return rc;
   if ((what & ADMM_TC_STATE) && (rc = tc_refresh_state(p, st))) return rc;
   return ADMM_OK;
 }

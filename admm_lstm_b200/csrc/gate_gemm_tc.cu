@@ -2,17 +2,18 @@
 //
 //   Z[n, (g,j)] = sum_k x_t[k,n] W_g[k,j] + sum_k h_{t-1}[k,n] U_g[k,j]
 //
-// computed on the 5th-generation tensor cores as an fp32-accurate 3xTF32 product
-//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (a_hi = tf32 truncation done by the MMA itself,
-//                                                  a_lo = a - a_hi kept in a side buffer, b_hi/b_lo
-//                                                  pre-split copies of the small weight matrices)
-// because plain TF32 breaks the 1e-4 parity bar.
+// computed on the 5th-generation tensor cores as an fp32-accurate split product of fp16 pairs
+//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (a_hi = fp16(a 2^sa), a_lo = fp16(a 2^sa - a_hi): 22 significand
+//                                                  bits per operand, the same as a TF32 pair, at twice the MMA rate
+//                                                  and half the operand bytes; power-of-two scales sa, sb keep both
+//                                                  halves in fp16's normal range and are undone in the epilogue)
+// because a plain TF32 / BF16 / FP16 product breaks the 1e-4 parity bar.
 //
 // Both operands are consumed in their native feature-major layout, i.e. MN-major for UMMA:
 //   A tile = 128 samples x BK features   (sample index contiguous in HBM)
 //   B tile = (4 gates x JC units) x BK   (unit index contiguous in HBM)
-// TMA (128B swizzle with 32B atoms, boxes of 32 floats x BK rows) lands them in the canonical MN-major layout, so
-// there is no transposed copy of the state or of the weights anywhere.
+// TMA (128B swizzle, boxes of 64 halfs x BK rows) lands them in the canonical MN-major layout, so there is no
+// transposed copy of the state or of the weights anywhere.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue (one thread per sample row and half of the tile's units; TMEM lane == sample,
@@ -21,6 +22,7 @@
 // closed forms as the CUDA-core path (admm_math.cuh); all its global accesses are 128-byte warp rows.
 // Two CTAs are resident per SM (2 x 256 TMEM columns), so one tile's epilogue overlaps the other's MMAs.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <map>
@@ -35,13 +37,12 @@ namespace admm {
 namespace {
 
 constexpr int BM = 128;        // samples per tile (UMMA M)
-constexpr int BK = 16;         // features per pipeline stage (2 UMMA k-steps of 8)
-constexpr int NSTAGE = 2;
-constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int CHUNK_BYTES = 32 * BK * 4;     // one TMA box: 32 floats (128 B) x BK rows
+constexpr int BK = 32;         // features per pipeline stage (2 UMMA k-steps of 16)
+constexpr int CHUNK_BYTES = 64 * BK * 2;     // one MN chunk: 64 halfs (128 B) x BK rows
+constexpr int SCALE_H = 11;    // h operand scale 2^11: |h| < 1 for t < T by construction, finite up to |h| < 32
 
 struct TcMaps {
-  CUtensorMap x, x_lo, h, h_lo;         // dims (ldn, K, slabs)
+  CUtensorMap x, x_lo, h, h_lo;         // fp16 hi / lo halves of x 2^sX and h 2^SCALE_H; dims (ldn, K, slabs)
   CUtensorMap wx_hi, wx_lo, wh_hi, wh_lo;   // dims (H, K, 4)
   CUtensorMap gx_hi, gx_lo;             // gradient of the probed weight, dims (H, Ksrc, 4)
 };
@@ -91,6 +92,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -108,34 +117,31 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, float (&v)[8]) {
 
 // MN-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
-// For 32-bit (tf32) MN-major operands the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (=1):
-// rows of 128 B (32 samples/units) per k, 32-byte units XOR-swizzled with (k mod 4); plain SWIZZLE_128B reads
-// as zeros (measured, scripts/tc_micro.cu).  TMA writes exactly this with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-// LBO = byte stride between 32-element chunks along MN, SBO = byte stride between 4-row groups along K.
+// 16-bit MN-major operands use plain SWIZZLE_128B (=2): rows of 128 B (64 samples/units) per k, 16-byte units
+// XOR-swizzled with (k mod 8) -- what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B.
+// LBO = byte stride between 64-element chunks along MN, SBO = byte stride between 8-row groups along K.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((uint32_t)(CHUNK_BYTES) >> 4) << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;
+  d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::tf32 instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, A MN-major [15],
+// kind::f16 instruction descriptor: D=F32 [4,6)=1, A=F16 [7,10)=0, B=F16 [10,13)=0, A MN-major [15],
 // B MN-major [16], N>>3 [17,23), M>>4 [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct Cfg {
   static constexpr int JC = 64;                       // hidden units per tile
   static constexpr int NCOL = 4 * JC;                 // accumulator columns: (gate, unit)
   static constexpr int TMEM_COLS = 256;
-  static constexpr int A_BYTES = BM * BK * 4;         // 8 KB
-  static constexpr int B_BYTES = NCOL * BK * 4;       // 16 KB
+  static constexpr int A_BYTES = BM * BK * 2;         // 8 KB  (one half of the pair)
+  static constexpr int B_BYTES = NCOL * BK * 2;       // 16 KB
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
 };
 
 // k-block range [kb_begin, kb_end) over the concatenated feature axis (x blocks first, then h blocks) and the
@@ -144,6 +150,17 @@ struct TcRange {
   int kb_begin, kb_end;
   int b_is_grad;      // 0: B = (wx | wh) hi/lo ; 1: B = gradient hi/lo, k relative to kb_begin
 };
+
+// fp16 pair of a state value v: hi = fp16(v 2^SCALE_H), lo = fp16(v 2^SCALE_H - hi)  (saturating, never inf)
+__device__ __forceinline__ void split_f16(float vs, __half* hi, __half* lo) {
+  const float c = fminf(fmaxf(vs, -65504.0f), 65504.0f);
+  const __half h = __float2half_rn(c);
+  *hi = h;
+  *lo = __float2half_rn(c - __half2float(h));
+}
+__device__ __forceinline__ void store_h16(__half* hi, __half* lo, float h) {
+  split_f16(h * (float)(1 << SCALE_H), hi, lo);
+}
 
 // Epilogue of one tile for the units [u_begin, u_end) (multiples of 8) of the calling warp's 32 sample rows: reads the
 // accumulator columns from TMEM (t_row = TMEM address of the warp's lane quarter, accumulator buffer included) and
@@ -161,10 +178,15 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
     // in flight per thread.  Loads use the streaming path (each state entry is touched once per launch).
     constexpr int EB = 2;
     const float rho_g[4] = {rho.i, rho.f, rho.g, rho.o};
+    const float acc_scale = *p.acc_scale;            // 2^-(sa + sb) of the operand pair of this launch
     for (int jb = u_begin; jb < u_end; jb += 8) {
       float z[4][8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) tmem_ld8(t_row + g * JC + jb, z[g]);
+      for (int g = 0; g < 4; ++g) {
+        tmem_ld8(t_row + g * JC + jb, z[g]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[g][i] *= acc_scale;
+      }
 #pragma unroll
       for (int eb = 0; eb < 8; eb += EB) {
         int64_t off[EB];
@@ -195,8 +217,9 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             if (p.gate[2]) __stcs(p.gate[2] + off[e], r.g);
             if (p.gate[3]) __stcs(p.gate[3] + off[e], r.o);
             __stcs(p.gate[4] + off[e], r.c);
-            p.gate[5][off[e]] = r.h;                         // h_t is the next timestep's A operand: keep it in L2
-            if (p.h_lo) p.h_lo[off[e]] = tf32_lo(r.h);
+            p.gate[5][off[e]] = r.h;
+            if (p.h_lo) p.h_lo[off[e]] = tf32_lo(r.h);       // tf32 pair of the A^T R reduction GEMM
+            store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h);   // fp16 pair: the next timestep's A operand
           }
         }
         if (MODE == GG_SWEEP) {
@@ -239,6 +262,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             if (!p.last) {
               p.gate[5][off[e]] = r.h;
               if (p.h_lo) p.h_lo[off[e]] = tf32_lo(r.h);
+              store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h);
             }
             __stcs(p.dual[0] + off[e], r.li); __stcs(p.dual[1] + off[e], r.lf); __stcs(p.dual[2] + off[e], r.lg);
             __stcs(p.dual[3] + off[e], r.lo); __stcs(p.dual[4] + off[e], r.lc);
@@ -294,139 +318,6 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
         }
       }
     }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, 2)
-gate_gemm_tc_kernel(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0, const TcRange rng) {
-  using C = Cfg;
-  constexpr int JC = C::JC;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float red[4 * 8];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // blockIdx.x walks the unit tiles: CTAs that share the same 128 samples (the A tile) are scheduled together, so the
-  // state is streamed from HBM once per launch and re-used from L2; the weights (a few MB) stay L2-resident anyway.
-  const int j0 = blockIdx.x * JC;
-  const int n0 = blockIdx.y * BM;
-  const int tl = blockIdx.z;
-  const int D = p.D, H = p.H;
-  const int nkx = (D + BK - 1) / BK, nkh = (H + BK - 1) / BK, nkb = nkx + nkh;
-
-  if (MODE == GG_RAWZ && p.done) {
-    if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
-  }
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&acc_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  (void)nkb;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
-        const int li = kb - rng.kb_begin;
-        const int s = li % NSTAGE, it = li / NSTAGE;
-        if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
-        const bool is_x = kb < nkx;
-        const int k0 = (is_x ? kb : kb - nkx) * BK;
-        uint8_t* st = smem + s * C::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES);
-        const CUtensorMap* ma = is_x ? &maps.x : &maps.h;
-        const CUtensorMap* ml = is_x ? &maps.x_lo : &maps.h_lo;
-        const int slab = slab0 + tl;
-        // one 4-D box per operand tile: dims (32 samples, features, 32-sample chunk, slab) land as [chunk][k][32]
-        tma_load_4d(st, ma, &full_bar[s], 0, k0, n0 / 32, slab);
-        tma_load_4d(st + C::A_BYTES, ml, &full_bar[s], 0, k0, n0 / 32, slab);
-        const CUtensorMap* bh = rng.b_is_grad ? &maps.gx_hi : (is_x ? &maps.wx_hi : &maps.wh_hi);
-        const CUtensorMap* bl = rng.b_is_grad ? &maps.gx_lo : (is_x ? &maps.wx_lo : &maps.wh_lo);
-        const int kb0 = rng.b_is_grad ? li * BK : k0;
-        uint8_t* sb = st + 2 * C::A_BYTES;
-        // dims (32 units, features, 32-unit chunk, gate): lands as [gate][chunk][k][32] = the (gate, unit) column order
-        tma_load_4d(sb, bh, &full_bar[s], 0, kb0, j0 / 32, 0);
-        tma_load_4d(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 32, 0);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, C::NCOL);
-      for (int kb = rng.kb_begin; kb < rng.kb_end; ++kb) {
-        const int li = kb - rng.kb_begin;
-        const int s = li % NSTAGE, it = li / NSTAGE;
-        mbar_wait(&full_bar[s], it & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + C::A_BYTES;
-        const uint32_t b_hi = st + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint32_t off = ks * 1024;
-          const uint32_t acc0 = (li > 0 || ks > 0) ? 1u : 0u;
-          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc0);
-          umma_tf32(tmem_base, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
-          umma_tf32(tmem_base, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
-        }
-        umma_commit(&empty_bar[s]);
-      }
-      umma_commit(&acc_bar);
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
-    const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
-    const int ehalf = (warp - 2) >> 2;                 // which 32 of the tile's 64 units this warp handles
-    const int row = quarter * 32 + lane;
-    const int64_t n = (int64_t)n0 + row;
-    const bool ok = n < p.n;
-    const int64_t ldn = p.ldn;
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const Rho rho = p.rho;
-    const int64_t soff = (int64_t)tl * p.s_tstride;
-    constexpr int NM = 4;
-    float msum[NM] = {0.f, 0.f, 0.f, 0.f};
-
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
-    epilogue_units<MODE>(p, t_row, ehalf * (JC / 2), (ehalf + 1) * (JC / 2), j0, n, ok, tl, msum);
-    tc_fence_before();
-    // block-level reduction of the metric partials over the 4 epilogue warps
-    if (MODE == GG_SWEEP || MODE == GG_GRAD) {
-      double* dst = (MODE == GG_SWEEP) ? p.metrics : p.fw_acc;
-      constexpr int NOUT = (MODE == GG_SWEEP) ? 3 : NM;
-      if (dst) {
-#pragma unroll
-        for (int k = 0; k < NOUT; ++k) {
-          const float s = warp_sum(msum[k]);
-          if (lane == 0) red[k * 8 + (warp - 2)] = s;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int et = threadIdx.x - 64;
-        if (et < NOUT) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) s += (double)red[et * 8 + w];
-          atomicAdd(dst + et, s);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -491,14 +382,14 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
           mbar_expect_tx(&full_bar[s], 2 * C::A_BYTES + 2 * C::B_BYTES);
           const CUtensorMap* ma = is_x ? &maps.x : &maps.h;
           const CUtensorMap* ml = is_x ? &maps.x_lo : &maps.h_lo;
-          tma_load_4d(st, ma, &full_bar[s], 0, k0, n0 / 32, slab);
-          tma_load_4d(st + C::A_BYTES, ml, &full_bar[s], 0, k0, n0 / 32, slab);
+          tma_load_4d(st, ma, &full_bar[s], 0, k0, n0 / 64, slab);
+          tma_load_4d(st + C::A_BYTES, ml, &full_bar[s], 0, k0, n0 / 64, slab);
           const CUtensorMap* bh = rng.b_is_grad ? &maps.gx_hi : (is_x ? &maps.wx_hi : &maps.wh_hi);
           const CUtensorMap* bl = rng.b_is_grad ? &maps.gx_lo : (is_x ? &maps.wx_lo : &maps.wh_lo);
           const int kb0 = rng.b_is_grad ? li * BK : k0;
           uint8_t* sb = st + 2 * C::A_BYTES;
-          tma_load_4d(sb, bh, &full_bar[s], 0, kb0, j0 / 32, 0);
-          tma_load_4d(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 32, 0);
+          tma_load_4d(sb, bh, &full_bar[s], 0, kb0, j0 / 64, 0);
+          tma_load_4d(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 64, 0);
         }
       }
     }
@@ -522,11 +413,11 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
           const uint32_t a_hi = st, a_lo = st + C::A_BYTES;
           const uint32_t b_hi = st + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint32_t off = ks * 1024;
-            umma_tf32(d_tmem, make_desc(a_hi + off), make_desc(b_hi + off), idesc, (li > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32(d_tmem, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
-            umma_tf32(d_tmem, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint32_t off = ks * 2048;                // 16 features = two 8-row swizzle groups
+            umma_f16(d_tmem, make_desc(a_hi + off), make_desc(b_hi + off), idesc, (li > 0 || ks > 0) ? 1u : 0u);
+            umma_f16(d_tmem, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);
+            umma_f16(d_tmem, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -604,27 +495,36 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// 4-D view of an fp32 tensor [outer][rows][cols] (cols contiguous) for MN-major operand tiles:
-// dims (32 cols-in-chunk, rows, cols/32 chunks, outer), box (32, BK, box_chunks, box_outer), SWIZZLE_128B_ATOM_32B,
-// zero fill out of bounds.  One box lands in shared memory as [outer][chunk][row][32], the canonical MN-major layout.
+// 4-D view of an fp16 tensor [outer][rows][cols] (cols contiguous) for MN-major operand tiles:
+// dims (64 cols-in-chunk, rows, cols/64 chunks, outer), box (64, BK, box_chunks, box_outer), SWIZZLE_128B, zero fill
+// out of bounds.  One box lands in shared memory as [outer][chunk][row][64], the canonical MN-major layout.
 int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t outer, uint64_t row_stride_elems,
              uint64_t outer_stride_elems, uint32_t box_chunks, uint32_t box_outer) {
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADMM_ECUDA; }
-  cuuint64_t dims[4] = {32, rows, (cols + 31) / 32, outer};
-  cuuint64_t strides[3] = {row_stride_elems * 4, 128, outer_stride_elems * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)BK, box_chunks, box_outer};
+  cuuint64_t dims[4] = {64, rows, (cols + 63) / 64, outer};
+  cuuint64_t strides[3] = {row_stride_elems * 2, 128, outer_stride_elems * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)BK, box_chunks, box_outer};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return ADMM_ECUDA; }
   return ADMM_OK;
 }
 
-// workspace layout (floats): [x_lo T*D*ldn][h_lo (T+1)*H*ldn][wx_hi 4DH][wx_lo 4DH][wh_hi 4HH][wh_lo 4HH][g_hi 4KmaxH][g_lo 4KmaxH]
+// Scales and maxima kept on the device, so that preparing an operand never synchronises with the host.
+struct TcMeta {
+  unsigned max_x, max_wx, max_wh, max_g, max_d;   // bit patterns of max |.| (non-negative floats order like unsigned)
+  int s_x;                                        // x is stored as fp16 pairs of x 2^s_x
+  float scale_z, scale_q, scale_d;                // 2^-(sa+sb): accumulator -> z (weights), Q (gradient), x dW (refresh)
+  int pad_[7];
+};
+
+// workspace layout in floats (fp16 buffers take half a float per element):
+// [x_lo][h_lo] tf32 low parts for the A^T R GEMM | fp16 pairs of x, h, wx, wh, g | TcMeta
 struct WsLayout {
-  int64_t x_lo, h_lo, wx_hi, wx_lo, wh_hi, wh_lo, g_hi, g_lo, total;
+  int64_t x_lo, h_lo, x16_hi, x16_lo, h16_hi, h16_lo, wx_hi, wx_lo, wh_hi, wh_lo, g_hi, g_lo, meta, total;
 };
 WsLayout ws_layout(const admm_problem* p) {
   WsLayout w;
@@ -632,13 +532,38 @@ WsLayout ws_layout(const admm_problem* p) {
   const int64_t kmax = D > H ? D : H;
   int64_t o = 0;
   auto take = [&](int64_t n) { const int64_t r = o; o += (n + 255) / 256 * 256; return r; };
+  auto take16 = [&](int64_t n) { return take((n + 1) / 2); };
   w.x_lo = take(T * D * ldn);
   w.h_lo = take((T + 1) * H * ldn);
-  w.wx_hi = take(4 * D * H); w.wx_lo = take(4 * D * H);
-  w.wh_hi = take(4 * H * H); w.wh_lo = take(4 * H * H);
-  w.g_hi = take(4 * kmax * H); w.g_lo = take(4 * kmax * H);
+  w.x16_hi = take16(T * D * ldn); w.x16_lo = take16(T * D * ldn);
+  w.h16_hi = take16((T + 1) * H * ldn); w.h16_lo = take16((T + 1) * H * ldn);
+  w.wx_hi = take16(4 * D * H); w.wx_lo = take16(4 * D * H);
+  w.wh_hi = take16(4 * H * H); w.wh_lo = take16(4 * H * H);
+  w.g_hi = take16(4 * kmax * H); w.g_lo = take16(4 * kmax * H);
+  w.meta = take(64);
   w.total = o;
   return w;
+}
+inline __half* ws_half(const admm_problem* p, int64_t off) { return reinterpret_cast<__half*>((float*)p->tc_ws + off); }
+inline TcMeta* ws_meta(const admm_problem* p) { return reinterpret_cast<TcMeta*>((float*)p->tc_ws + ws_layout(p).meta); }
+
+// Largest power-of-two exponent c with m 2^c < 2^13 (0 for m = 0 / non-finite): both halves of the pair then sit high
+// in fp16's normal range and 2^13 * 2^13 * K stays far from fp32 overflow in the accumulator.
+__device__ __forceinline__ int cap_exp(unsigned max_bits) {
+  const float m = __uint_as_float(max_bits);
+  if (!(m > 0.f) || !isfinite(m)) return 0;
+  int e;
+  frexpf(m, &e);            // m = f 2^e, f in [0.5, 1)
+  return 13 - e;
+}
+
+__global__ void absmax_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, unsigned* out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(b ? a[i] - b[i] : a[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
 __global__ void split_trunc_kernel(const float* __restrict__ src, float* __restrict__ lo, int64_t n) {
@@ -652,14 +577,42 @@ __global__ void split_trunc_kernel(const float* __restrict__ src, float* __restr
     for (int64_t k = i; k < n; ++k) lo[k] = tf32_lo(src[k]);
   }
 }
-// weights: hi = round-to-nearest tf32 (the MMA then truncates an already-representable value), lo = w - hi
-__global__ void split_round_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = src[i];
-  const float h = tf32_round(v);
-  hi[i] = h;
-  lo[i] = tf32_round(v - h);
+
+// What a conversion launch prepares.  The exponents are recomputed by every thread from the device-side maxima.
+enum PrepKind { PREP_X = 0, PREP_H = 1, PREP_WX = 2, PREP_WH = 3, PREP_GRAD_X = 4, PREP_GRAD_H = 5, PREP_DELTA = 6 };
+
+__global__ void prep_f16_kernel(int kind, const float* __restrict__ a, const float* __restrict__ b, __half* __restrict__ hi,
+                                __half* __restrict__ lo, int64_t n, TcMeta* meta) {
+  int ex = 0;            // element scale exponent
+  if (kind == PREP_X) {
+    ex = cap_exp(meta->max_x);
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta->s_x = ex;
+  } else if (kind == PREP_H) {
+    ex = SCALE_H;
+  } else if (kind == PREP_WX || kind == PREP_WH) {
+    // one accumulator holds x W + h U: s_x + s_wx == SCALE_H + s_wh == S
+    const int sx = cap_exp(meta->max_x);
+    const int S = min(sx + cap_exp(meta->max_wx), SCALE_H + cap_exp(meta->max_wh));
+    ex = (kind == PREP_WX) ? S - sx : S - SCALE_H;
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta->scale_z = ldexpf(1.0f, -S);
+  } else if (kind == PREP_GRAD_X || kind == PREP_GRAD_H) {
+    ex = cap_exp(meta->max_g);
+    const int sa = (kind == PREP_GRAD_X) ? cap_exp(meta->max_x) : SCALE_H;
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta->scale_q = ldexpf(1.0f, -(sa + ex));
+  } else {               // PREP_DELTA: x (W_new - W_old)
+    ex = cap_exp(meta->max_d);
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta->scale_d = ldexpf(1.0f, -(cap_exp(meta->max_x) + ex));
+  }
+  const float sc = ldexpf(1.0f, ex);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = (b ? a[i] - b[i] : a[i]) * sc;
+    split_f16(v, hi + i, lo + i);
+  }
+}
+
+unsigned prep_grid(int64_t n) {
+  const int64_t b = (n + 255) / 256;
+  return (unsigned)(b < 148 * 8 ? (b < 1 ? 1 : b) : 148 * 8);
 }
 
 struct MapKey {
@@ -680,72 +633,50 @@ int get_maps(const admm_problem* p, int grad_src, TcMaps* out) {
   if (it == g_maps.end()) {
     if (g_maps.size() > 64) g_maps.clear();
     TcMaps m;
-    float* ws = (float*)p->tc_ws;
     const WsLayout w = ws_layout(p);
     const uint64_t ldn = p->ldn, T = p->T, D = p->D, H = p->H;
     int rc = 0;
-    rc |= make_map(&m.x, p->x, ldn, D, T, ldn, D * ldn, BM / 32, 1);
-    rc |= make_map(&m.x_lo, ws + w.x_lo, ldn, D, T, ldn, D * ldn, BM / 32, 1);
-    rc |= make_map(&m.h, p->gate[5], ldn, H, T + 1, ldn, H * ldn, BM / 32, 1);
-    rc |= make_map(&m.h_lo, ws + w.h_lo, ldn, H, T + 1, ldn, H * ldn, BM / 32, 1);
-    rc |= make_map(&m.wx_hi, ws + w.wx_hi, H, D, 4, H, D * H, Cfg::JC / 32, 4);
-    rc |= make_map(&m.wx_lo, ws + w.wx_lo, H, D, 4, H, D * H, Cfg::JC / 32, 4);
-    rc |= make_map(&m.wh_hi, ws + w.wh_hi, H, H, 4, H, H * H, Cfg::JC / 32, 4);
-    rc |= make_map(&m.wh_lo, ws + w.wh_lo, H, H, 4, H, H * H, Cfg::JC / 32, 4);
+    rc |= make_map(&m.x, ws_half(p, w.x16_hi), ldn, D, T, ldn, D * ldn, BM / 64, 1);
+    rc |= make_map(&m.x_lo, ws_half(p, w.x16_lo), ldn, D, T, ldn, D * ldn, BM / 64, 1);
+    rc |= make_map(&m.h, ws_half(p, w.h16_hi), ldn, H, T + 1, ldn, H * ldn, BM / 64, 1);
+    rc |= make_map(&m.h_lo, ws_half(p, w.h16_lo), ldn, H, T + 1, ldn, H * ldn, BM / 64, 1);
+    rc |= make_map(&m.wx_hi, ws_half(p, w.wx_hi), H, D, 4, H, D * H, Cfg::JC / 64, 4);
+    rc |= make_map(&m.wx_lo, ws_half(p, w.wx_lo), H, D, 4, H, D * H, Cfg::JC / 64, 4);
+    rc |= make_map(&m.wh_hi, ws_half(p, w.wh_hi), H, H, 4, H, H * H, Cfg::JC / 64, 4);
+    rc |= make_map(&m.wh_lo, ws_half(p, w.wh_lo), H, H, 4, H, H * H, Cfg::JC / 64, 4);
     if (rc) return ADMM_ECUDA;
     it = g_maps.emplace(key, m).first;
   }
   *out = it->second;
   // the gradient maps depend on src (K = D or H); they are cheap to encode per call
   const WsLayout w = ws_layout(p);
-  float* ws = (float*)p->tc_ws;
   const uint64_t K = (grad_src == ADMM_SRC_X) ? p->D : p->H, H = p->H;
-  int rc = make_map(&out->gx_hi, ws + w.g_hi, H, K, 4, H, K * H, Cfg::JC / 32, 4);
-  rc |= make_map(&out->gx_lo, ws + w.g_lo, H, K, 4, H, K * H, Cfg::JC / 32, 4);
+  int rc = make_map(&out->gx_hi, ws_half(p, w.g_hi), H, K, 4, H, K * H, Cfg::JC / 64, 4);
+  rc |= make_map(&out->gx_lo, ws_half(p, w.g_lo), H, K, 4, H, K * H, Cfg::JC / 64, 4);
   return rc ? ADMM_ECUDA : ADMM_OK;
-}
-
-bool use_persistent() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ADMM_TC_PERSISTENT");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
 }
 
 template <int MODE>
 int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, int slab0, int tc, const TcRange& rng,
               cudaStream_t st) {
   using C = Cfg;
-  if (use_persistent()) {
-    static bool configured_p = false;
-    if (!configured_p) {
-      cudaFuncSetAttribute(gate_gemm_tc_persistent<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
-      configured_p = true;
-    }
-    static int n_sm = 0;
-    if (!n_sm) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
-    const int n_jt = p->H / C::JC, n_nt = (int)(p->ldn / BM);
-    const int n_tiles = n_jt * n_nt * tc;
-    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    gate_gemm_tc_persistent<MODE><<<grid, P_THREADS, P_SMEM_BYTES, st>>>(a, maps, slab0, rng, n_jt, n_nt, n_tiles);
-    count_launch();
-    return check_launch("gate_gemm_tc_persistent");
+  static bool configured_p = false;
+  if (!configured_p) {
+    cudaFuncSetAttribute(gate_gemm_tc_persistent<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    configured_p = true;
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(gate_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    configured = true;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  dim3 grid((unsigned)(p->H / C::JC), (unsigned)(p->ldn / BM), (unsigned)tc);
-  gate_gemm_tc_kernel<MODE><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a, maps, slab0, rng);
+  const int n_jt = p->H / C::JC, n_nt = (int)(p->ldn / BM);
+  const int n_tiles = n_jt * n_nt * tc;
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  gate_gemm_tc_persistent<MODE><<<grid, P_THREADS, P_SMEM_BYTES, st>>>(a, maps, slab0, rng, n_jt, n_nt, n_tiles);
   count_launch();
-  return check_launch("gate_gemm_tc");
+  return check_launch("gate_gemm_tc_persistent");
 }
 
 }  // namespace
@@ -759,23 +690,45 @@ int64_t tc_workspace_bytes(const admm_problem* p) {
   return ws_layout(p).total * 4;
 }
 
+namespace {
+// max |a - b| (b may be null) -> *slot, then the fp16 pair of the scaled values
+int prep_operand(int kind, const float* a, const float* b, __half* hi, __half* lo, int64_t n, TcMeta* meta, unsigned* slot,
+                 cudaStream_t st) {
+  if (slot) {
+    if (cudaMemsetAsync(slot, 0, sizeof(unsigned), st) != cudaSuccess) return check_launch("prep memset");
+    absmax_kernel<<<prep_grid(n), 256, 0, st>>>(a, b, n, slot);
+    count_launch();
+  }
+  prep_f16_kernel<<<prep_grid(n), 256, 0, st>>>(kind, a, b, hi, lo, n, meta);
+  count_launch();
+  return check_launch("prep_f16");
+}
+}  // namespace
+
 int tc_refresh_weights(const admm_problem* p, cudaStream_t st) {
   const WsLayout w = ws_layout(p);
-  float* ws = (float*)p->tc_ws;
+  TcMeta* meta = ws_meta(p);
   const int64_t nx = 4LL * p->D * p->H, nh = 4LL * p->H * p->H;
-  split_round_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(p->wx, ws + w.wx_hi, ws + w.wx_lo, nx);
-  split_round_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(p->wh, ws + w.wh_hi, ws + w.wh_lo, nh);
+  // both maxima first: the common accumulator scale depends on both
+  if (cudaMemsetAsync(&meta->max_wx, 0, 2 * sizeof(unsigned), st) != cudaSuccess) return check_launch("prep memset");
+  absmax_kernel<<<prep_grid(nx), 256, 0, st>>>(p->wx, nullptr, nx, &meta->max_wx);
+  absmax_kernel<<<prep_grid(nh), 256, 0, st>>>(p->wh, nullptr, nh, &meta->max_wh);
   count_launch(2);
-  return check_launch("tc_refresh_weights");
+  int rc = prep_operand(PREP_WX, p->wx, nullptr, ws_half(p, w.wx_hi), ws_half(p, w.wx_lo), nx, meta, nullptr, st);
+  if (rc) return rc;
+  return prep_operand(PREP_WH, p->wh, nullptr, ws_half(p, w.wh_hi), ws_half(p, w.wh_lo), nh, meta, nullptr, st);
 }
 
 int tc_refresh_inputs(const admm_problem* p, cudaStream_t st) {
   const WsLayout w = ws_layout(p);
   float* ws = (float*)p->tc_ws;
+  TcMeta* meta = ws_meta(p);
   const int64_t nx = (int64_t)p->T * p->D * p->ldn;
   split_trunc_kernel<<<(unsigned)((nx / 4 + 255) / 256 + 1), 256, 0, st>>>(p->x, ws + w.x_lo, nx);
   count_launch();
-  return check_launch("tc_refresh_inputs");
+  int rc = prep_operand(PREP_X, p->x, nullptr, ws_half(p, w.x16_hi), ws_half(p, w.x16_lo), nx, meta, &meta->max_x, st);
+  if (rc) return rc;
+  return tc_refresh_weights(p, st);        // the weights' scales are tied to the scale of x
 }
 
 int tc_refresh_state(const admm_problem* p, cudaStream_t st) {
@@ -784,36 +737,29 @@ int tc_refresh_state(const admm_problem* p, cudaStream_t st) {
   const int64_t nh = (int64_t)(p->T + 1) * p->H * p->ldn;
   split_trunc_kernel<<<(unsigned)((nh / 4 + 255) / 256 + 1), 256, 0, st>>>(p->gate[5], ws + w.h_lo, nh);
   count_launch();
-  return check_launch("tc_refresh_state");
+  return prep_operand(PREP_H, p->gate[5], nullptr, ws_half(p, w.h16_hi), ws_half(p, w.h16_lo), nh, ws_meta(p), nullptr, st);
 }
 
-__global__ void split_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ hi,
-                                  float* __restrict__ lo, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = a[i] - b[i];
-  const float h = tf32_round(v);
-  hi[i] = h;
-  lo[i] = tf32_round(v - h);
-}
-
-// operand slot <- hi/lo split of (x2g - wx_prev): what the h-phase adds to the stored pre-activations
+// operand slot <- fp16 pair of (x2g - wx_prev): what the h-phase adds to the stored pre-activations
 int tc_refresh_wx_delta(const admm_problem* p, cudaStream_t st) {
   const WsLayout w = ws_layout(p);
-  float* ws = (float*)p->tc_ws;
+  TcMeta* meta = ws_meta(p);
   const int64_t n = 4LL * p->D * p->H;
-  split_diff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->wx, p->wx_prev, ws + w.g_hi, ws + w.g_lo, n);
-  count_launch();
-  return check_launch("tc_refresh_wx_delta");
+  return prep_operand(PREP_DELTA, p->wx, p->wx_prev, ws_half(p, w.g_hi), ws_half(p, w.g_lo), n, meta, &meta->max_d, st);
 }
 
 int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStream_t st) {
   const WsLayout w = ws_layout(p);
-  float* ws = (float*)p->tc_ws;
+  TcMeta* meta = ws_meta(p);
   const int64_t n = 4LL * (src == ADMM_SRC_X ? p->D : p->H) * p->H;
-  split_round_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad, ws + w.g_hi, ws + w.g_lo, n);
-  count_launch();
-  return check_launch("tc_refresh_grad");
+  return prep_operand(src == ADMM_SRC_X ? PREP_GRAD_X : PREP_GRAD_H, grad, nullptr, ws_half(p, w.g_hi), ws_half(p, w.g_lo), n,
+                      meta, &meta->max_g, st);
+}
+
+void tc_h16(const admm_problem* p, __half** hi, __half** lo) {
+  const WsLayout w = ws_layout(p);
+  *hi = ws_half(p, w.h16_hi);
+  *lo = ws_half(p, w.h16_lo);
 }
 
 float* tc_h_lo(const admm_problem* p) {
@@ -831,6 +777,14 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   const int64_t slab_elems = (int64_t)p->H * p->ldn;
   const int slab0 = (int)((a.h_prev - p->gate[5]) / slab_elems);
   a.h_lo = tc_h_lo(p) + (a.gate[5] - p->gate[5]);
+  {
+    __half *hi, *lo;
+    tc_h16(p, &hi, &lo);
+    a.h16_hi = hi + (a.gate[5] - p->gate[5]);
+    a.h16_lo = lo + (a.gate[5] - p->gate[5]);
+  }
+  const TcMeta* meta = ws_meta(p);
+  a.acc_scale = z_refresh ? &meta->scale_d : &meta->scale_z;
   const int nkx = (p->D + BK - 1) / BK, nkh = (p->H + BK - 1) / BK;
   const TcRange full{0, nkx + nkh, 0};
   switch (mode) {
@@ -849,6 +803,7 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
       }
       GateGemmArgs q = a;
       q.scratch = a.scratch_q;
+      q.acc_scale = &meta->scale_q;
       const TcRange qr = (a.src == ADMM_SRC_X) ? TcRange{0, nkx, 1} : TcRange{nkx, nkx + nkh, 1};
       return launch_tc<GG_RAWZ>(p, q, maps, slab0, tc, qr, st);
     }

@@ -452,7 +452,7 @@ def main():
         # x_t, h_{t-1}, 10 state reads (+c_{t-1}), 11 state writes; +4H when the sweep also stores z_t for the next
         # iteration's x-phase gradient (admm_problem::z_valid)
         bytes_sweep = ((26.0 if opt.keeps_preactivations else 22.0) * H + D) * 4
-        tc_ceiling = peaks["bf16_tflops_sustained"] / 6.0   # tf32 = bf16/2 dense, and three MMAs per product
+        tc_ceiling = peaks["bf16_tflops_sustained"] / 3.0   # fp16 pairs at the bf16/fp16 dense rate, three MMAs per product
         roofline = None
         if "admm_sweep_t" in ksum:
             calls, tot_ms = ksum["admm_sweep_t"]
@@ -463,17 +463,17 @@ def main():
             if tensor_bound and opt.uses_tensor_cores:
                 roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"],
                             "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
-                            "frac_of_3xtf32_ceiling": achieved_tf / tc_ceiling, "hbm_gbs": achieved_gb}
+                            "frac_of_3xfp16_ceiling": achieved_tf / tc_ceiling, "hbm_gbs": achieved_gb}
             else:
                 roofline = {"bound": "hbm", "achieved": achieved_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": achieved_gb / peaks["hbm_gbs"], "traffic": None, "useful_tflops": achieved_tf}
-            roofline.update({"kernel": ("gate_gemm_tc_kernel<SWEEP>" if opt.uses_tensor_cores else "gate_gemm_simt_kernel<SWEEP>")
+            roofline.update({"kernel": ("gate_gemm_tc_persistent<SWEEP>" if opt.uses_tensor_cores else "gate_gemm_simt_kernel<SWEEP>")
                                        + " via admm_sweep_t (one launch per timestep)",
                              "avg_launch_ms": avg_ms, "launches_timed": calls,
                              "share_of_step": tot_ms / ksteps / ms_step, "peak_source": peaks["source"],
                              "algorithmic_per_launch": {"flops": flops_gate * opt.n_local, "bytes": bytes_sweep * opt.n_local},
                              "note": "useful fp32-equivalent flops against the measured dense bf16 peak (sustained); the kernel "
-                                     "computes an fp32-accurate 3xTF32 product, whose ceiling is peak/6"})
+                                     "computes an fp32-accurate product of fp16 pairs (3 MMAs), whose ceiling is peak/3"})
         if roofline is not None:
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tpath):

@@ -13,7 +13,7 @@ opt = ADMMBasedOptimizer(model, (torch.from_numpy(x), torch.from_numpy(y)), benc
                          keep_preactivations=False)
 out = torch.empty(4 * H * opt.ldn, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
-for mode, name in ((1, "tcgen05 3xTF32"), (0, "fp32 CUDA-core")):
+for mode, name in ((1, "tcgen05 3xFP16"), (0, "fp32 CUDA-core")):
     for _ in range(3): opt._call("admm_debug_preact", opt._pp, 2, out.data_ptr(), mode, s)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20 if mode else 3

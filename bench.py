@@ -218,7 +218,7 @@ def bench_admm_l(args, rank, world, local_rank, config, metric, unit):
             ach = flops / (per_step_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                        "frac_of_3xtf32_ceiling": ach / (peaks["bf16_tflops_sustained"] / 6.0),
+                        "frac_of_3xtf32_ceiling": ach / (peaks["bf16_tflops_sustained"] / 6.0),   # the A^T R kernel still runs 3xTF32
                         "kernel": "atr_tc_kernel (Gram / right-hand-side sums) via admm_l_sums, packing kernel included",
                         "ms_per_step": per_step_ms, "calls_per_step": calls // 2, "share_of_step": per_step_ms / ms_step,
                         "peak_source": peaks["source"], "algorithmic_per_step": {"flops": flops},

@@ -41,6 +41,8 @@ struct LSlot {
   float* h_lo;           // tf32 low part of h at slot s, or nullptr
   __half* h16_hi;        // fp16 pair of h 2^11 at slot s (the gate GEMM's A operand), or nullptr
   __half* h16_lo;
+  unsigned* bound_track; // tensor-core path: running max of |z_g + lambda_s,g/rho_s| and |h| (bit pattern): the bound
+                         // that scales the fp16 operand of the next iteration's Gram / right-hand-side pass
   admm_l_hyper hp;
 };
 
@@ -51,6 +53,13 @@ __device__ __forceinline__ void l_store_h_side(const LSlot& p, int64_t idx, floa
   const __half hh = __float2half_rn(c);
   p.h16_hi[idx] = hh;
   p.h16_lo[idx] = __float2half_rn(c - __half2float(hh));
+}
+
+__device__ __forceinline__ void track_bound(unsigned* slot, float b) {
+  if (!slot) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(b));
 }
 
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -72,19 +81,26 @@ __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
 // main.py:89-100 from P: z, gates, c, h
 __global__ void __launch_bounds__(NT) l_forward_kernel(const LSlot p) {
   const int64_t total = (int64_t)p.H * p.ldn;
+  float bmax = 0.f;
   for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
     const int64_t n = idx % p.ldn;
     if (n >= p.n) continue;
     float zz[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) { zz[g] = p.P[(int64_t)g * total + idx]; p.z[g][idx] = zz[g]; }
+    for (int g = 0; g < 4; ++g) {
+      zz[g] = p.P[(int64_t)g * total + idx];
+      p.z[g][idx] = zz[g];
+      bmax = fmaxf(bmax, fabsf(zz[g]));
+    }
     const float i = l_sig(zz[0]), f = l_sig(zz[1]), gg = tanhf(zz[2]), o = l_sig(zz[3]);
     const float c = f * p.c_prev[idx] + i * gg;
     const float h = o * tanhf(c);
     p.gate[0][idx] = i; p.gate[1][idx] = f; p.gate[2][idx] = gg; p.gate[3][idx] = o;
     p.gate[4][idx] = c; p.gate[5][idx] = h;
     l_store_h_side(p, idx, h);
+    bmax = fmaxf(bmax, fabsf(h));
   }
+  track_bound(p.bound_track, bmax);
 }
 
 // ---------------------------------------------------------------------------------------------------- packing
@@ -98,10 +114,22 @@ struct LPack {
   float rho_s;
   float* r;               // [5H][tc][ldn]
   float* r_lo;
+  __half* r16_hi;         // fp16-pair variant (tensor-core path): rows scaled by 2^cap(*r_bound)
+  __half* r16_lo;
+  const unsigned* r_bound;
 };
+// exponent c with m 2^c < 2^13 (the same rule as cap_exp() of gate_gemm_tc.cu: producer and consumer must agree)
+__device__ __forceinline__ int l_cap_exp(unsigned max_bits) {
+  const float m = __uint_as_float(max_bits);
+  if (!(m > 0.f) || !isfinite(m)) return 0;
+  int e;
+  frexpf(m, &e);
+  return 13 - e;
+}
 __global__ void __launch_bounds__(NT) l_pack_kernel(const LPack p) {
   const int64_t per_t = (int64_t)p.H * p.ldn;
   const int64_t total = per_t * p.tc;
+  const float r_scale = p.r16_hi ? ldexpf(1.0f, l_cap_exp(*p.r_bound)) : 1.0f;
   for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
     const int tl = (int)(idx / per_t);
     const int64_t rem = idx % per_t;
@@ -118,8 +146,15 @@ __global__ void __launch_bounds__(NT) l_pack_kernel(const LPack p) {
 #pragma unroll
     for (int g = 0; g < 5; ++g) {
       const int64_t ro = (((int64_t)g * p.H + j) * p.tc + tl) * p.ldn + n;
-      p.r[ro] = v[g];
-      p.r_lo[ro] = tf32_lo(v[g]);
+      if (p.r16_hi) {
+        const float c = fminf(fmaxf(v[g] * r_scale, -65504.0f), 65504.0f);
+        const __half hh = __float2half_rn(c);
+        p.r16_hi[ro] = hh;
+        p.r16_lo[ro] = __float2half_rn(c - __half2float(hh));
+      } else {
+        p.r[ro] = v[g];
+        p.r_lo[ro] = tf32_lo(v[g]);
+      }
     }
   }
 }
@@ -232,22 +267,25 @@ __device__ __forceinline__ LDualIn l_duals_load(const LSlot& p, int64_t idx, int
   }
   return d;
 }
-__device__ __forceinline__ void l_duals_store(const LSlot& p, int64_t idx, const LDualIn& d, float c, float h, float c_) {
+__device__ __forceinline__ float l_duals_store(const LSlot& p, int64_t idx, const LDualIn& d, float c, float h, float c_) {
   const float rs = p.hp.rho_s, rp = p.hp.rho_p, r9 = p.hp.rho9, r10 = p.hp.rho10;
   const float n10 = d.l10 + r10 * (tanhf(c) * d.o - h);
   const float n9 = d.l9 + r9 * (c - d.g * d.i - c_ * d.f);
   const float gv[4] = {d.i, d.f, d.g, d.o};
   float np_[4], ns_[4];
+  float b = fabsf(h);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float act = (q == 2) ? tanhf(d.z[q]) : l_sig(d.z[q]);
     np_[q] = d.lp[q] + rp * (act - gv[q]);
     ns_[q] = d.ls[q] + rs * (d.z[q] - d.P[q]);
+    b = fmaxf(b, fabsf(d.z[q] + ns_[q] / rs));          // |V| of the next packing pass (l_pack_kernel)
   }
   p.lam10[idx] = n10;
   p.lam9[idx] = n9;
 #pragma unroll
   for (int q = 0; q < 4; ++q) { p.lam_p[q][idx] = np_[q]; p.lam_s[q][idx] = ns_[q]; }
+  return b;
 }
 
 // update_c (:223-241), update_h for s < T (:249-250), then the duals.  LAST: c only.
@@ -257,6 +295,7 @@ __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* 
   const float r9 = p.hp.rho9, r10 = p.hp.rho10;
   const float appro_h = appro_tanh(red_max[4]);
   const float qua_o = (float)red_sum[0];
+  float bmax = 0.f;
   for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
     if (idx % p.ldn >= p.n) continue;
     const LDualIn d = l_duals_load(p, idx, total);
@@ -275,9 +314,10 @@ __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* 
       p.gate[4][idx] = c;
       p.gate[5][idx] = hn;
       l_store_h_side(p, idx, hn);
-      l_duals_store(p, idx, d, c, hn, c_);
+      bmax = fmaxf(bmax, l_duals_store(p, idx, d, c, hn, c_));
     }
   }
+  if (!LAST) track_bound(p.bound_track, bmax);
 }
 
 // ---------------------------------------------------------------------------------------------------- t = T-1
@@ -319,11 +359,13 @@ __global__ void __launch_bounds__(NT) l_last_a_kernel(const float* h, const floa
 }
 __global__ void __launch_bounds__(NT) l_duals_kernel(const LSlot p) {
   const int64_t total = (int64_t)p.H * p.ldn;
+  float bmax = 0.f;
   for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
     if (idx % p.ldn >= p.n) continue;
     const LDualIn d = l_duals_load(p, idx, total);
-    l_duals_store(p, idx, d, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx]);
+    bmax = fmaxf(bmax, l_duals_store(p, idx, d, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx]));
   }
+  track_bound(p.bound_track, bmax);
 }
 
 // ---------------------------------------------------------------------------------------------------- host helpers
@@ -358,8 +400,9 @@ LSlot make_slot(const admm_l_problem* lp, int s, const float* P) {
   k.lam9 = lp->lam9 + (int64_t)s * slab;
   k.lam10 = lp->lam10 + (int64_t)s * slab;
   k.P = P;
-  k.h_lo = nullptr; k.h16_hi = k.h16_lo = nullptr;
+  k.h_lo = nullptr; k.h16_hi = k.h16_lo = nullptr; k.bound_track = nullptr;
   if (b.tc_ws && tc_eligible(&b)) {
+    k.bound_track = tc_r_bound(&b);
     k.h_lo = tc_h_lo(&b) + (int64_t)s * slab;
     tc_h16(&b, &k.h16_hi, &k.h16_lo);
     k.h16_hi += (int64_t)s * slab;
@@ -367,6 +410,13 @@ LSlot make_slot(const admm_l_problem* lp, int s, const float* P) {
   }
   k.hp = lp->hp;
   return k;
+}
+
+int reset_bound(const admm_l_problem* lp, cudaStream_t st) {
+  const admm_problem& b = lp->base;
+  if (!(b.tc_ws && tc_eligible(&b))) return ADMM_OK;
+  if (cudaMemsetAsync(tc_r_bound(&b), 0, sizeof(unsigned), st) != cudaSuccess) return check_launch("bound memset");
+  return ADMM_OK;
 }
 
 int gemm_P(const admm_l_problem* lp, int s, float* scratch, cudaStream_t st) {
@@ -389,6 +439,7 @@ int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, void* stre
   if (rc) return rc;
   ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch, "admm_l_forward_t: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (s == 1 && (rc = reset_bound(lp, st))) return rc;
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch);
   l_forward_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k);
@@ -415,14 +466,23 @@ int admm_l_sums(const admm_l_problem* lp, int t0, int tc, float* scratch, double
   k.n = b.n; k.ldn = b.ldn; k.H = b.H; k.tc = tc; k.t0 = t0;
   for (int g = 0; g < 4; ++g) { k.z[g] = lp->z[g]; k.lam_s[g] = lp->lam_s[g]; }
   k.h = b.gate[5]; k.rho_s = lp->hp.rho_s; k.r = scratch; k.r_lo = scratch + half;
+  const bool use_tc = b.tc_ws && tc_eligible(&b);
+  // fp16 pairs when both reduction GEMMs can take the tensor-core path (row count a multiple of the 128-row tile, D >= 8)
+  const bool f16 = use_tc && (5 * b.H) % 128 == 0 && b.D >= 8;
+  k.r16_hi = k.r16_lo = nullptr; k.r_bound = nullptr;
+  if (f16) {
+    k.r16_hi = reinterpret_cast<__half*>(scratch);
+    k.r16_lo = reinterpret_cast<__half*>(scratch + half);
+    k.r_bound = tc_r_bound(&b);
+  }
   l_pack_kernel<<<ew_grid((int64_t)b.H * b.ldn * tc), NT, 0, st>>>(k);
   count_launch();
   if ((rc = check_launch("l_pack"))) return rc;
-  const bool use_tc = b.tc_ws && tc_eligible(&b);
   AtrArgs r;
   memset(&r, 0, sizeof(r));
   r.ldn = b.ldn; r.H = b.H; r.tc = tc; r.rows = 5 * b.H; r.rpg = b.H;
   r.scratch = scratch; r.scratch_lo = use_tc ? scratch + half : nullptr;
+  if (f16) { r.r16_hi = k.r16_hi; r.r16_lo = k.r16_lo; r.r_bound = k.r_bound; }
   // src = x: P_x[g] and S_xh
   r.K = b.D; r.a_src = b.x + (int64_t)t0 * b.D * b.ldn; r.a_tstride = (int64_t)b.D * b.ldn; r.g_acc = acc_x;
   rc = use_tc ? atr_tc(&b, r, st) : atr_simt(r, st);
@@ -475,6 +535,7 @@ int admm_l_sweep_max(const admm_l_problem* lp, int s, float* scratch, float* red
   if (rc) return rc;
   ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max, "admm_l_sweep_max: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (s == 1 && (rc = reset_bound(lp, st))) return rc;       // the sweep re-measures the bound of the next packing pass
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch);
   l_max_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k, red_max);

@@ -159,8 +159,13 @@ int admm_weight_begin(const admm_problem* p, int src, void* stream) {
   int rc = validate(p, "admm_weight_begin");
   if (rc) return rc;
   ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_begin: bad src");
-  if (src == ADMM_SRC_H && p->zstore && p->wx_prev && p->tc_ws && tc_eligible(p))
-    return tc_refresh_wx_delta(p, (cudaStream_t)stream);
+  const bool use_tc = p->tc_ws && tc_eligible(p);
+  if (src == ADMM_SRC_X && use_tc) {
+    // the x-phase gradient pass measures the bound on |R| that scales the h-phase's fp16 A^T R operand
+    if (cudaMemsetAsync(tc_r_bound(p), 0, sizeof(unsigned), (cudaStream_t)stream) != cudaSuccess)
+      return check_launch("r_bound memset");
+  }
+  if (src == ADMM_SRC_H && p->zstore && p->wx_prev && use_tc) return tc_refresh_wx_delta(p, (cudaStream_t)stream);
   return ADMM_OK;
 }
 
@@ -177,6 +182,15 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   const bool atr_on_tc = use_tc;
   a.scratch = scratch; a.tc = tc; a.fw_acc = fw_acc; a.src = src;
   a.scratch_q = atr_on_tc ? scratch + 4LL * p->H * tc * p->ldn : nullptr;     // tf32 low part of R^T
+  // tensor-core path: the x-phase (K = D, cheap) keeps 3xTF32 and measures max(1 + |lambda/rho| + |gate|) >= |R|; the
+  // h-phase (K = H) writes R^T as fp16 pairs scaled from that bound and runs the fp16 A^T R GEMM
+  const bool r16 = use_tc && src == ADMM_SRC_H;
+  if (use_tc && src == ADMM_SRC_X) a.bound_track = tc_r_bound(p);
+  if (r16) {
+    a.r_bound = tc_r_bound(p);
+    a.r16_hi = reinterpret_cast<__half*>(scratch);
+    a.r16_lo = reinterpret_cast<__half*>(a.scratch_q);
+  }
   if (use_tc && p->zstore && p->wx_prev) {
     // x-phase: full GEMM, z kept; h-phase: z <- z + x (W_new - W_old), no full GEMM
     a.zstore = p->zstore; a.zT = p->T; a.zt0 = t0;
@@ -189,7 +203,7 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
     e.n = p->n; e.ldn = p->ldn; e.H = p->H; e.tc = tc; e.zT = p->T; e.zt0 = t0; e.zstore = p->zstore;
     for (int g = 0; g < 4; ++g) { e.gate[g] = a.gate[g]; e.dual[g] = a.dual[g]; e.rho[g] = p->hp.rho[g]; }
     e.s_tstride = a.s_tstride;
-    e.r = a.scratch; e.r_lo = a.scratch_q; e.fw_acc = fw_acc;
+    e.r = a.scratch; e.r_lo = a.scratch_q; e.fw_acc = fw_acc; e.bound_track = a.bound_track;
     rc = grad_from_z(e, st);
   } else {
     rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
@@ -203,6 +217,7 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   r.a_src = (src == ADMM_SRC_X) ? a.x : a.h_prev;
   r.a_tstride = (int64_t)r.K * p->ldn;
   r.scratch = scratch; r.g_acc = g_acc;
+  if (r16) { r.r16_hi = a.r16_hi; r.r16_lo = a.r16_lo; r.r_bound = a.r_bound; }
   if (atr_on_tc) return atr_tc(p, r, st);
   return atr_simt(r, st);
 }

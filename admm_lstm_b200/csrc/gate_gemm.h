@@ -42,6 +42,12 @@ struct GateGemmArgs {
   __half* h16_hi;        // slab t of the fp16 pair of h 2^11 (tensor-core path): the gate GEMM's A operand
   __half* h16_lo;
   const float* acc_scale;  // tensor-core path: 2^-(sa+sb) that turns the accumulator of this launch into z or Q
+  // GRAD on the tensor-core path.  x-phase: bound_track receives max (1 + |lambda/rho| + |gate|) >= |R| (bit pattern,
+  // atomicMax).  h-phase: R^T is written as an fp16 pair of R 2^sR (sR from *r_bound) for the fp16 A^T R GEMM.
+  unsigned* bound_track;
+  const unsigned* r_bound;
+  __half* r16_hi;
+  __half* r16_lo;
 };
 
 int gate_gemm_simt(int mode, const GateGemmArgs& a, int tc, cudaStream_t st);
@@ -59,6 +65,11 @@ struct AtrArgs {
   // Generalisation used by the Gram / right-hand-side sums of ADMM-LSTM-L: R has `rows` rows (0 = the default 4*H)
   // in groups of `rpg` (0 = H): G_acc[c / rpg][k][c % rpg] += sum A_src[k][n] R[c][n].
   int32_t rows, rpg;
+  // fp16-pair variant (tensor-core path): R^T as fp16 pairs of R 2^sR, sR = cap(*r_bound); A_src from the fp16 pairs
+  // of x / h kept by the tensor-core workspace.  nullptr -> 3xTF32 on `scratch` / `scratch_lo`.
+  const __half* r16_hi;
+  const __half* r16_lo;
+  const unsigned* r_bound;
 };
 int atr_simt(const AtrArgs& a, cudaStream_t st);
 
@@ -97,6 +108,7 @@ struct GradFromZArgs {
   float* r;               // [4][H][tc][ldn]
   float* r_lo;
   double* fw_acc;         // [4]
+  unsigned* bound_track;  // max (1 + |lambda/rho| + |gate|) over the elements read (bit pattern, atomicMax) or nullptr
 };
 int grad_from_z(const GradFromZArgs& a, cudaStream_t st);
 

@@ -151,6 +151,16 @@ struct TcRange {
   int b_is_grad;      // 0: B = (wx | wh) hi/lo ; 1: B = gradient hi/lo, k relative to kb_begin
 };
 
+// Largest power-of-two exponent c with m 2^c < 2^13 (0 for m = 0 / non-finite): both halves of the pair then sit high
+// in fp16's normal range and 2^13 * 2^13 * K stays far from fp32 overflow in the accumulator.
+__device__ __forceinline__ int cap_exp(unsigned max_bits) {
+  const float m = __uint_as_float(max_bits);
+  if (!(m > 0.f) || !isfinite(m)) return 0;
+  int e;
+  frexpf(m, &e);            // m = f 2^e, f in [0.5, 1)
+  return 13 - e;
+}
+
 // fp16 pair of a state value v: hi = fp16(v 2^SCALE_H), lo = fp16(v 2^SCALE_H - hi)  (saturating, never inf)
 __device__ __forceinline__ void split_f16(float vs, __half* hi, __half* lo) {
   const float c = fminf(fmaxf(vs, -65504.0f), 65504.0f);
@@ -167,7 +177,7 @@ __device__ __forceinline__ void store_h16(__half* hi, __half* lo, float h) {
 // applies the closed forms of admm_math.cuh with coalesced (lane == sample) global accesses.
 template <int MODE>
 __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t_row, int u_begin, int u_end, int j0,
-                                               int64_t n, bool ok, int tl, float (&msum)[4]) {
+                                               int64_t n, bool ok, int tl, float (&msum)[5]) {
   constexpr int JC = Cfg::JC;
   const int H = p.H;
   const int64_t ldn = p.ldn;
@@ -178,6 +188,8 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
     // in flight per thread.  Loads use the streaming path (each state entry is touched once per launch).
     constexpr int EB = 2;
     const float rho_g[4] = {rho.i, rho.f, rho.g, rho.o};
+    const float inv_rho_g[4] = {1.0f / rho.i, 1.0f / rho.f, 1.0f / rho.g, 1.0f / rho.o};
+    const float r_scale = (MODE == GG_GRAD && p.r16_hi) ? ldexpf(1.0f, cap_exp(*p.r_bound)) : 1.0f;
     const float acc_scale = *p.acc_scale;            // 2^-(sa + sb) of the operand pair of this launch
     for (int jb = u_begin; jb < u_end; jb += 8) {
       float z[4][8];
@@ -302,6 +314,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
               const float rr = grad_point<FastMath>(zz[g], lam[g][e], gv[g][e], rho_g[g], g == 2, &u);
               rv[g] = ok ? rr : 0.f;
               if (ok) msum[g] += u * u;
+              if (p.bound_track) msum[4] = fmaxf(msum[4], 1.0f + fabsf(lam[g][e]) * inv_rho_g[g] + fabsf(gv[g][e]));
             }
             if (p.tc < 0) {            // never taken
               if (rv[0] == 123.456f) p.scratch[off[e]] = rv[0] + rv[1] + rv[2] + rv[3] + zz[0] + zz[1] + zz[2] + zz[3];
@@ -311,8 +324,12 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             for (int g = 0; g < 4; ++g) {
               const int64_t so = (((int64_t)g * H + (j0 + jb + eb + e)) * p.tc + tl) * ldn + n;
               if (p.zstore) __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, zz[g]);
-              p.scratch[so] = rv[g];                         // read right back by the A^T R GEMM: keep in L2
-              if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv[g]);
+              if (p.r16_hi) {                                // h-phase: fp16 pair for the fp16 A^T R GEMM
+                split_f16(rv[g] * r_scale, p.r16_hi + so, p.r16_lo + so);
+              } else {
+                p.scratch[so] = rv[g];                       // read right back by the A^T R GEMM: keep in L2
+                if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv[g]);
+              }
             }
           }
         }
@@ -430,7 +447,7 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
     const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
     const int ugrp = ew >> 2;                          // 4 warps per lane quarter: 16 of the tile's 64 units each
     const int row = quarter * 32 + lane;
-    float msum[4] = {0.f, 0.f, 0.f, 0.f};
+    float msum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // [4] = running max of the |R| bound (GRAD, x-phase)
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int j0 = (tile % n_jt) * JC;
@@ -447,6 +464,12 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
       if (lane == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[buf])) : "memory");
       }
+    }
+    if (MODE == GG_GRAD && p.bound_track) {
+      float b = msum[4];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+      if (lane == 0) atomicMax(p.bound_track, __float_as_uint(b));
     }
     if (MODE == GG_SWEEP || MODE == GG_GRAD) {
       double* dst = (MODE == GG_SWEEP) ? p.metrics : p.fw_acc;
@@ -518,7 +541,8 @@ struct TcMeta {
   unsigned max_x, max_wx, max_wh, max_g, max_d;   // bit patterns of max |.| (non-negative floats order like unsigned)
   int s_x;                                        // x is stored as fp16 pairs of x 2^s_x
   float scale_z, scale_q, scale_d;                // 2^-(sa+sb): accumulator -> z (weights), Q (gradient), x dW (refresh)
-  int pad_[7];
+  unsigned r_bound;                               // bound on |R| of the A^T R operand (bit pattern), see GateGemmArgs
+  int pad_[6];
 };
 
 // workspace layout in floats (fp16 buffers take half a float per element):
@@ -546,16 +570,6 @@ WsLayout ws_layout(const admm_problem* p) {
 }
 inline __half* ws_half(const admm_problem* p, int64_t off) { return reinterpret_cast<__half*>((float*)p->tc_ws + off); }
 inline TcMeta* ws_meta(const admm_problem* p) { return reinterpret_cast<TcMeta*>((float*)p->tc_ws + ws_layout(p).meta); }
-
-// Largest power-of-two exponent c with m 2^c < 2^13 (0 for m = 0 / non-finite): both halves of the pair then sit high
-// in fp16's normal range and 2^13 * 2^13 * K stays far from fp32 overflow in the accumulator.
-__device__ __forceinline__ int cap_exp(unsigned max_bits) {
-  const float m = __uint_as_float(max_bits);
-  if (!(m > 0.f) || !isfinite(m)) return 0;
-  int e;
-  frexpf(m, &e);            // m = f 2^e, f in [0.5, 1)
-  return 13 - e;
-}
 
 __global__ void absmax_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, unsigned* out) {
   float m = 0.f;
@@ -756,6 +770,8 @@ int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStrea
                       meta, &meta->max_g, st);
 }
 
+unsigned* tc_r_bound(const admm_problem* p) { return &ws_meta(p)->r_bound; }
+
 void tc_h16(const admm_problem* p, __half** hi, __half** lo) {
   const WsLayout w = ws_layout(p);
   *hi = ws_half(p, w.h16_hi);
@@ -818,7 +834,7 @@ namespace {
 // Both operands are contiguous along the reduction index n, i.e. K-major for UMMA: plain SWIZZLE_128B boxes of
 // 32 samples.  D rows (TMEM lanes) = 128 consecutive (gate, unit) columns of G, D columns = NT rows k of G, so the
 // epilogue's accumulation into the fp64 G buffer is coalesced along j.  3xTF32: R_hi*h_hi + R_lo*h_hi + R_hi*h_lo.
-constexpr int ATR_BKN = 32;           // samples per pipeline stage (one 128-byte swizzle row)
+constexpr int ATR_BKN = 32;           // tf32: samples per pipeline stage (one 128-byte swizzle row); fp16 pairs: 64
 constexpr int ATR_STAGES = 2;
 constexpr int ATR_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
@@ -836,13 +852,21 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_kmajor(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc_kmajor_f16(int m, int n) {      // kind::f16, A = B = F16, D = F32
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
-template <int NT_>
+// F16: operands are fp16 pairs (R 2^sR from the GRAD epilogue / packing kernel, x 2^sx or h 2^11 from the workspace),
+// 64 samples per 128-byte row, kind::f16 MMAs with K = 16; the accumulator is rescaled by 2^-(sR + sa) in the epilogue.
+// Same bytes per stage as the tf32 variant for twice the samples: the kernel is bound by operand delivery.
+template <int NT_, bool F16>
 __global__ void __launch_bounds__(ATR_THREADS, 1)
 atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H, int tc, int64_t ldn, int slab0,
-              int chunks_per_cta, int n_chunks, int use_atomics) {   // H = rows per group of R (AtrArgs::rpg)
-  constexpr int A_BYTES = 128 * ATR_BKN * 4;        // R tile   16 KB
-  constexpr int B_BYTES = NT_ * ATR_BKN * 4;        // h tile   NT x 128 B
+              int chunks_per_cta, int n_chunks, int use_atomics, const unsigned* r_bound, const unsigned* a_max) {
+  // H = rows per group of R (AtrArgs::rpg); a_max = max|x| bits when A_src = x (scale 2^cap), nullptr for h (2^SCALE_H)
+  constexpr int BKN = F16 ? 64 : ATR_BKN;
+  constexpr int A_BYTES = 128 * 128;                // R tile   128 rows x 128 B
+  constexpr int B_BYTES = NT_ * 128;                // h tile   NT rows x 128 B
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -854,7 +878,7 @@ atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H,
   const int ch_begin = blockIdx.z * chunks_per_cta;
   const int ch_end = min(ch_begin + chunks_per_cta, n_chunks);
   if (ch_begin >= ch_end) return;
-  const int chunks_per_t = (int)(ldn / ATR_BKN);
+  const int chunks_per_t = (int)(ldn / BKN);
   constexpr int TCOLS = NT_ < 32 ? 32 : NT_;
 
   if (threadIdx.x == 0) {
@@ -873,7 +897,7 @@ atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H,
       for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int li = ch - ch_begin, s = li % ATR_STAGES, it = li / ATR_STAGES;
         if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
-        const int tl = ch / chunks_per_t, n0 = (ch % chunks_per_t) * ATR_BKN;
+        const int tl = ch / chunks_per_t, n0 = (ch % chunks_per_t) * BKN;
         uint8_t* st = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_3d(st, &maps.r, &full_bar[s], n0, tl, c0);
@@ -884,7 +908,7 @@ atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H,
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_kmajor(128, NT_);
+      constexpr uint32_t idesc = F16 ? make_idesc_kmajor_f16(128, NT_) : make_idesc_kmajor(128, NT_);
       for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int li = ch - ch_begin, s = li % ATR_STAGES, it = li / ATR_STAGES;
         mbar_wait(&full_bar[s], it & 1);
@@ -892,11 +916,18 @@ atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H,
         const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t r_hi = st, r_lo = st + A_BYTES, h_hi = st + 2 * A_BYTES, h_lo = h_hi + B_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < ATR_BKN / 8; ++ks) {
-          const uint32_t off = ks * 32;                 // 8 floats inside the 128-byte swizzle row
-          umma_tf32(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_hi + off), idesc, (li > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, make_desc_k128(r_lo + off), make_desc_k128(h_hi + off), idesc, 1u);
-          umma_tf32(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_lo + off), idesc, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t off = ks * 32;                 // 8 floats / 16 halfs inside the 128-byte swizzle row
+          const uint32_t acc0 = (li > 0 || ks > 0) ? 1u : 0u;
+          if (F16) {
+            umma_f16(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_hi + off), idesc, acc0);
+            umma_f16(tmem_base, make_desc_k128(r_lo + off), make_desc_k128(h_hi + off), idesc, 1u);
+            umma_f16(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_lo + off), idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_hi + off), idesc, acc0);
+            umma_tf32(tmem_base, make_desc_k128(r_lo + off), make_desc_k128(h_hi + off), idesc, 1u);
+            umma_tf32(tmem_base, make_desc_k128(r_hi + off), make_desc_k128(h_lo + off), idesc, 1u);
+          }
         }
         umma_commit(&empty_bar[s]);
       }
@@ -907,6 +938,8 @@ atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H,
     const int c = c0 + quarter * 32 + lane;            // (gate, unit) column of G owned by this thread
     const int g = c / H, j = c % H;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    double out_scale = 1.0;
+    if (F16) out_scale = (double)ldexpf(1.0f, -(cap_exp(*r_bound) + (a_max ? cap_exp(*a_max) : SCALE_H)));
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
     for (int kb = 0; kb < NT_; kb += 8) {
@@ -917,8 +950,9 @@ atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H,
         const int k = k0 + kb + e;
         if (k < K) {
           double* dst = g_acc + ((int64_t)g * K + k) * H + j;
-          if (use_atomics) atomicAdd(dst, (double)v[e]);
-          else *dst += (double)v[e];
+          const double val = (double)v[e] * out_scale;
+          if (use_atomics) atomicAdd(dst, val);
+          else *dst += val;
         }
       }
     }
@@ -932,45 +966,50 @@ atr_tc_kernel(const __grid_constant__ AtrMaps maps, double* g_acc, int K, int H,
 }
 
 int make_map_box(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                 uint64_t stride2_elems, uint32_t b0, uint32_t b1, uint32_t b2) {
+                 uint64_t stride2_elems, uint32_t b0, uint32_t b1, uint32_t b2, bool f16 = false) {
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADMM_ECUDA; }
+  const uint64_t eb = f16 ? 2 : 4;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {stride1_elems * 4, stride2_elems * 4};
+  cuuint64_t strides[2] = {stride1_elems * eb, stride2_elems * eb};
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base),
+                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (atr) failed (%d)", (int)r); return ADMM_ECUDA; }
   return ADMM_OK;
 }
 
-template <int NT_>
+template <int NT_, bool F16>
 int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x, cudaStream_t st) {
-  constexpr int SMEM = ATR_STAGES * (2 * 128 * ATR_BKN * 4 + 2 * NT_ * ATR_BKN * 4) + 1024;
+  constexpr int SMEM = ATR_STAGES * (2 * 128 * 128 + 2 * NT_ * 128) + 1024;
+  constexpr int BKN = F16 ? 64 : ATR_BKN;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(atr_tc_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(atr_tc_kernel<NT_, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     configured = true;
   }
   AtrMaps m;
+  const WsLayout w = ws_layout(p);
   const uint64_t ldn = a.ldn, H = a.H, tc = a.tc, T1 = p->T + 1;
   const uint64_t rows = a.rows ? a.rows : 4 * H;
   const int rpg = a.rpg ? a.rpg : a.H;
   int rc = 0;
-  rc |= make_map_box(&m.r, a.scratch, ldn, tc, rows, ldn, tc * ldn, ATR_BKN, 1, 128);
-  rc |= make_map_box(&m.r_lo, a.scratch_lo, ldn, tc, rows, ldn, tc * ldn, ATR_BKN, 1, 128);
+  rc |= make_map_box(&m.r, F16 ? (const void*)a.r16_hi : (const void*)a.scratch, ldn, tc, rows, ldn, tc * ldn, BKN, 1, 128, F16);
+  rc |= make_map_box(&m.r_lo, F16 ? (const void*)a.r16_lo : (const void*)a.scratch_lo, ldn, tc, rows, ldn, tc * ldn, BKN, 1, 128, F16);
   if (src_is_x) {     // A_src = x: [T][D][ldn]; rows k >= D are zero-filled by TMA and masked in the epilogue
     const uint64_t D = p->D;
-    rc |= make_map_box(&m.h, p->x, ldn, D, p->T, ldn, D * ldn, ATR_BKN, NT_, 1);
-    rc |= make_map_box(&m.h_lo, (float*)p->tc_ws + ws_layout(p).x_lo, ldn, D, p->T, ldn, D * ldn, ATR_BKN, NT_, 1);
+    rc |= make_map_box(&m.h, F16 ? (const void*)ws_half(p, w.x16_hi) : (const void*)p->x, ldn, D, p->T, ldn, D * ldn, BKN, NT_, 1, F16);
+    rc |= make_map_box(&m.h_lo, F16 ? (const void*)ws_half(p, w.x16_lo) : (const void*)((float*)p->tc_ws + w.x_lo), ldn, D, p->T,
+                       ldn, D * ldn, BKN, NT_, 1, F16);
   } else {
-    rc |= make_map_box(&m.h, p->gate[5], ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
-    rc |= make_map_box(&m.h_lo, tc_h_lo(p), ldn, H, T1, ldn, H * ldn, ATR_BKN, NT_, 1);
+    rc |= make_map_box(&m.h, F16 ? (const void*)ws_half(p, w.h16_hi) : (const void*)p->gate[5], ldn, H, T1, ldn, H * ldn, BKN, NT_, 1, F16);
+    rc |= make_map_box(&m.h_lo, F16 ? (const void*)ws_half(p, w.h16_lo) : (const void*)tc_h_lo(p), ldn, H, T1, ldn, H * ldn, BKN,
+                       NT_, 1, F16);
   }
   if (rc) return ADMM_ECUDA;
-  const int n_chunks = (int)(tc * (ldn / ATR_BKN));
+  const int n_chunks = (int)(tc * (ldn / BKN));
   const int tiles = (int)((rows / 128) * ((a.K + NT_ - 1) / NT_));
   int splits = (148 + tiles - 1) / tiles;
   if (tiles * splits > 148 && splits > 1) --splits;          // stay within one wave of 148 single-CTA SMs
@@ -978,28 +1017,36 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
   const int cpc = (n_chunks + splits - 1) / splits;
   splits = (n_chunks + cpc - 1) / cpc;
   dim3 grid((unsigned)(rows / 128), (unsigned)((a.K + NT_ - 1) / NT_), (unsigned)splits);
-  atr_tc_kernel<NT_><<<grid, ATR_THREADS, SMEM, st>>>(m, a.g_acc, a.K, rpg, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1);
+  const unsigned* a_max = src_is_x ? &ws_meta(p)->max_x : nullptr;
+  atr_tc_kernel<NT_, F16><<<grid, ATR_THREADS, SMEM, st>>>(m, a.g_acc, a.K, rpg, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1,
+                                                           a.r_bound, a_max);
   count_launch();
   return check_launch("atr_tc");
+}
+
+template <int NT_>
+int launch_atr_any(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x, cudaStream_t st) {
+  if (a.r16_hi) return launch_atr<NT_, true>(p, a, slab0, src_is_x, st);
+  return launch_atr<NT_, false>(p, a, slab0, src_is_x, st);
 }
 
 }  // namespace
 
 // Tensor-core G += A_src^T R.  `a.a_src` must be a slab of p->gate[5] (src = h, K = H) or of p->x (src = x, K = D).
 int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st) {
-  if (!a.scratch_lo || ((a.rows ? a.rows : 4 * a.H) % 128) != 0) return atr_simt(a, st);
+  if ((!a.scratch_lo && !a.r16_hi) || ((a.rows ? a.rows : 4 * a.H) % 128) != 0) return atr_simt(a, st);
   const bool src_is_x = (a.a_src >= p->x && a.a_src < p->x + (int64_t)p->T * p->D * p->ldn);
   if (src_is_x) {
     if (p->D < 8) return atr_simt(a, st);               // a handful of rows: not worth a 64-row MMA tile
     const int slab0 = (int)((a.a_src - p->x) / ((int64_t)p->D * p->ldn));
-    if (a.K > 128) return launch_atr<256>(p, a, slab0, true, st);
-    if (a.K > 64) return launch_atr<128>(p, a, slab0, true, st);
-    return launch_atr<64>(p, a, slab0, true, st);
+    if (a.K > 128) return launch_atr_any<256>(p, a, slab0, true, st);
+    if (a.K > 64) return launch_atr_any<128>(p, a, slab0, true, st);
+    return launch_atr_any<64>(p, a, slab0, true, st);
   }
   const int slab0 = (int)((a.a_src - p->gate[5]) / ((int64_t)p->H * p->ldn));
-  if (p->H >= 256) return launch_atr<256>(p, a, slab0, false, st);
-  if (p->H >= 128) return launch_atr<128>(p, a, slab0, false, st);
-  return launch_atr<64>(p, a, slab0, false, st);
+  if (p->H >= 256) return launch_atr_any<256>(p, a, slab0, false, st);
+  if (p->H >= 128) return launch_atr_any<128>(p, a, slab0, false, st);
+  return launch_atr_any<64>(p, a, slab0, false, st);
 }
 
 }  // namespace admm

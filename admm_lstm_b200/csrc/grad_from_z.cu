@@ -18,7 +18,8 @@ __global__ void __launch_bounds__(NT) grad_from_z_kernel(const GradFromZArgs p, 
   __shared__ float red[NT / 32];
   const int g = blockIdx.y;
   const float rho = p.rho[g];
-  float fsum = 0.f;
+  float fsum = 0.f, bmax = 0.f;
+  const float inv_rho = 1.0f / rho;
   for (int64_t item = blockIdx.x; item < items_per_gate; item += gridDim.x) {
     const int nb = (int)(item % n_nb);
     const int64_t row = item / n_nb;                 // (unit j, timestep tl)
@@ -40,9 +41,15 @@ __global__ void __launch_bounds__(NT) grad_from_z_kernel(const GradFromZArgs p, 
       r[e] = ok ? rr : 0.f;
       rl[e] = tf32_lo(r[e]);
       if (ok) fsum = fmaf(u, u, fsum);
+      bmax = fmaxf(bmax, 1.0f + fabsf(lam[e]) * inv_rho + fabsf(gv[e]));     // >= |u| >= |R| for any z
     }
     *reinterpret_cast<float4*>(p.r + ro) = make_float4(r[0], r[1], r[2], r[3]);       // re-read at once by atr: keep in L2
     *reinterpret_cast<float4*>(p.r_lo + ro) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+  }
+  if (p.bound_track) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(p.bound_track, __float_as_uint(bmax));
   }
   const float s = warp_sum(fsum);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;

@@ -153,7 +153,9 @@ int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream);
  *           2 = window exhausted), [8,12) the exponent concerned.
  *  apply  : w <- (0.5 rho T theta w - G)/(beta + 0.5 rho theta T)           (admm.py:340-343)
  * K = D for ADMM_SRC_X, H for ADMM_SRC_H. */
-/* begin: once per `src` before the first admm_weight_grad of the phase (prepares the zstore refresh operands). */
+/* begin: once per `src` before the first admm_weight_grad of the phase (prepares the zstore refresh operands).
+ * Tensor-core path: the x-phase gradient pass also measures max(1 + |lambda/rho| + |gate|) >= |R|, the bound that scales
+ * the fp16 operand of the h-phase's A^T R GEMM -- run the x-phase of an iteration before its h-phase (admm.py:64-69 does). */
 int admm_weight_begin(const admm_problem* p, int src, void* stream);
 int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scratch,
                      double* g_acc, double* fw_acc, void* stream);

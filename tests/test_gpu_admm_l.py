@@ -125,3 +125,79 @@ def test_l_demo_surface(tmp_path, monkeypatch):
     np.testing.assert_allclose(out["val_loss"], ref["val_loss"][:6], rtol=1e-3)
     m = torch.load(tmp_path / "SAVED_MODELS" / "ADMM-LSTM-L.pt", weights_only=False)
     assert [n for n, _ in m.named_parameters()] == ["W_hi", "W_ii", "W_hf", "W_if", "W_ho", "W_io", "W_hg", "W_ig", "W_y"]
+
+
+@pytest.mark.parametrize("shape,tc", [((301, 4, 5, 12), False), ((600, 3, 16, 128), True)])
+def test_l_sharded_fake_world_equals_single(shape, tc):
+    """Two sample shards stepped by two threads whose all-reduces (SUM of the Gram / RHS sums, MAX and SUM of the
+    per-timestep scalars) are an in-process rendezvous must reproduce the unsharded run."""
+    _need_gpu()
+    import threading
+    n, t, dd, h = shape
+    rng = np.random.default_rng(7)
+    x, y = rng.random((n, t, dd), dtype=np.float32), rng.random((n, 1), dtype=np.float32)
+    d = {"init_Wy": (rng.standard_normal((h, 1)) * 0.1).astype(np.float32)}
+    for g in GATES:
+        d[f"init_W{g}"] = (rng.standard_normal((dd, h)) * 0.1).astype(np.float32)
+        d[f"init_U{g}"] = (rng.standard_normal((h, h)) * 0.1).astype(np.float32)
+    ref = make_opt(d, x, y, use_tensor_cores=tc, n_norm=float(n))
+
+    class FakeComm:
+        def __init__(self, rank, shared):
+            self.active, self.world_size, self.rank, self.shared = True, 2, rank, shared
+
+        def _reduce(self, t, op):
+            torch.cuda.current_stream().synchronize()
+            self.shared["buf"][self.rank] = t
+            self.shared["bar"].wait()
+            total = op(self.shared["buf"][0], self.shared["buf"][1])
+            self.shared["bar"].wait()
+            t.copy_(total)
+            self.shared["bar"].wait()
+
+        def allreduce_sum_(self, *tensors):
+            for t in tensors:
+                self._reduce(t, torch.add)
+
+        def allreduce_max_(self, *tensors):
+            for t in tensors:
+                self._reduce(t, torch.maximum)
+
+        def shard_range(self, n_total):
+            half = (n_total + 1) // 2
+            return (0, half) if self.rank == 0 else (half, n_total)
+
+        def sum_int(self, v, device):
+            return v
+
+    shared = {"buf": [None, None], "bar": threading.Barrier(2)}
+    opts, errs = [None, None], []
+
+    def worker(rank):
+        try:
+            torch.cuda.set_device(0)
+            o = make_opt(d, x, y, use_tensor_cores=tc, n_norm=float(n), comm=FakeComm(rank, shared), sharding="slice")
+            opts[rank] = o
+            for _ in range(3):
+                o.step()
+            torch.cuda.synchronize()
+        except Exception as exc:   # pragma: no cover
+            errs.append(exc)
+            shared["bar"].abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in (0, 1)]
+    [t_.start() for t_ in th]
+    [t_.join() for t_ in th]
+    assert not errs, errs
+    for _ in range(3):
+        ref.step()
+    wr = {k: v.cpu().numpy() for k, v in ref.weights().items()}
+    w0 = {k: v.cpu().numpy() for k, v in opts[0].weights().items()}
+    w1 = {k: v.cpu().numpy() for k, v in opts[1].weights().items()}
+    for k in wr:
+        assert np.array_equal(w0[k], w1[k]), k            # replicas stay bit-identical
+        assert rel(w0[k], wr[k]) < 2e-5, (k, rel(w0[k], wr[k]))
+    full = ref.state()["h"].cpu().numpy()
+    half = opts[0].n_local
+    assert rel(opts[0].state()["h"].cpu().numpy(), full[:half]) < 2e-5
+    assert rel(opts[1].state()["h"].cpu().numpy(), full[half:]) < 2e-5

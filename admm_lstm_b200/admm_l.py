@@ -66,6 +66,48 @@ class LSTM_L(nn.Module):
         return h_t @ self.W_y
 
 
+def exit_theta(ratio: torch.Tensor, theta0: float) -> torch.Tensor:
+    """Exit of `while Func2 > Func1: theta *= 2` for a quadratic subproblem: the smallest theta0 * 2^k (k >= 0) with
+    theta >= ratio, ratio = rho <G, S G> / ||G||^2 (NaN for G = 0 -> theta0).  No host synchronisation."""
+    ratio = torch.nan_to_num(ratio, nan=0.0, posinf=0.0)
+    k = torch.clamp(torch.ceil(torch.log2(torch.clamp(ratio / theta0, min=1e-300))), min=0.0)
+    return theta0 * torch.pow(torch.tensor(2.0, dtype=torch.float64, device=ratio.device), k)
+
+
+def l_weight_phase(s_xx, ax, ah, stt, pt, wx, wh, wy, *, rho_s, rho11, lam_w, lam_u, thetas=None) -> None:
+    """W_y, then (W, U) per gate in the order g, o, i, f (main.py:140-148) from the reduced Gram / right-hand-side sums,
+    in place on the fp32 weights `wx [4,D,H]`, `wh [4,H,H]`, `wy [H]` (storage order i, f, g, o).  fp64 algebra on
+    replicated data; device-agnostic (the CPU tests drive it with sums computed from the oracle's state).
+
+      ax[g] = sum_t x_t^T V_g,t (g < 4), ax[4] = S_xh;  ah[g] = sum_t h_{t-1}^T V_g,t, ah[4] = S_hh;
+      stt = h_T^T h_T;  pt = h_T^T (a + lambda11/rho11);  V_g = z_g + lambda_g/rho   (admm_lstm.py:76-163)."""
+    f64 = torch.float64
+    thetas = thetas if thetas is not None else {}
+    s_xh, s_hh = ax[4], 0.5 * (ah[4] + ah[4].t())
+    s_tt = 0.5 * (stt + stt.t())
+    # update_Wy (:92-104): theta0 = 0.01, Wy <- Wy + g/theta (no regulariser)
+    wy64 = wy.to(f64)
+    g = rho11 * (pt - s_tt @ wy64)
+    th = exit_theta(rho11 * (g @ (s_tt @ g)) / (g @ g), 0.01)
+    thetas["wy"] = th
+    wy.copy_(wy + g.float() / th.float())
+    # update_W / update_U (:107-163): w <- (theta w - G)/(lambda0 + theta)
+    for gname in _UPDATE_ORDER:
+        q = _ORDER.index(gname)
+        w, u = wx[q].to(f64), wh[q].to(f64)
+        gw = rho_s * (s_xx @ w + s_xh @ u - ax[q])
+        th = exit_theta(rho_s * (gw * (s_xx @ gw)).sum() / (gw * gw).sum(), 1.0)
+        thetas["W" + gname] = th
+        thf = th.float()
+        wx[q].copy_((thf * wx[q] - gw.float()) / (lam_w + thf))
+        w = wx[q].to(f64)
+        gu = rho_s * (s_xh.t() @ w + s_hh @ u - ah[q])
+        th = exit_theta(rho_s * (gu * (s_hh @ gu)).sum() / (gu * gu).sum(), 1.0)
+        thetas["U" + gname] = th
+        thf = th.float()
+        wh[q].copy_((thf * wh[q] - gu.float()) / (lam_u + thf))
+
+
 class ADMMLOptimizer(object):
     """State and iteration of ADMM-LSTM-L.
 
@@ -205,13 +247,6 @@ class ADMMLOptimizer(object):
         T, tc = self.seq_len, self._tc_chunk
         return [(t0, min(tc, T - t0)) for t0 in range(0, T, tc)]
 
-    @staticmethod
-    def _exit_theta(ratio: torch.Tensor, theta0: float) -> torch.Tensor:
-        """Smallest theta0 * 2^k (k >= 0) with theta >= ratio; ratio = rho <G, S G> / ||G||^2 (NaN for G = 0 -> theta0)."""
-        ratio = torch.nan_to_num(ratio, nan=0.0, posinf=0.0)
-        k = torch.clamp(torch.ceil(torch.log2(torch.clamp(ratio / theta0, min=1e-300))), min=0.0)
-        return theta0 * torch.pow(torch.tensor(2.0, dtype=torch.float64, device=ratio.device), k)
-
     # ------------------------------------------------------------------------------------------ iteration
     def step(self) -> None:
         """One iteration of main.py:139-188."""
@@ -229,39 +264,15 @@ class ADMMLOptimizer(object):
             self._call("admm_l_sums", lpp, t0, tc, self._scratch.data_ptr(), ax.data_ptr(), ah.data_ptr(), st)
         self._call("admm_l_sums_last", lpp, stt.data_ptr(), pt.data_ptr(), st)
         self.comm.allreduce_sum_(self._sums)
-        ax, ah, stt = ax.view(5, D, H), ah.view(5, H, H), stt.view(H, H)
-        s_xx, s_xh, s_hh = self._sxx, ax[4], 0.5 * (ah[4] + ah[4].t())
-        s_tt = 0.5 * (stt + stt.t())
-
-        # ---- W_y (update_Wy, admm_lstm.py:76-104): theta0 = 0.01, Wy <- Wy + g/theta
-        wy = self._wy.to(f64)
-        g = float(hp.rho11) * (pt - s_tt @ wy)
-        th = self._exit_theta(float(hp.rho11) * (g @ (s_tt @ g)) / (g @ g), 0.01)
-        self.thetas["wy"] = th
-        self._wy.copy_(self._wy + g.float() / th.float())
-
-        # ---- W then U per gate (update_W / update_U, :107-163): w <- (theta w - G)/(lambda0 + theta)
-        rho = float(hp.rho_s)
-        for gname in _UPDATE_ORDER:
-            q = _ORDER.index(gname)
-            w, u = self._wx[q].to(f64), self._wh[q].to(f64)
-            gw = rho * (s_xx @ w + s_xh @ u - ax[q])
-            th = self._exit_theta(rho * (gw * (s_xx @ gw)).sum() / (gw * gw).sum(), 1.0)
-            self.thetas["W" + gname] = th
-            thf = th.float()
-            self._wx[q].copy_((thf * self._wx[q] - gw.float()) / (float(hp.lam_w) + thf))
-            w = self._wx[q].to(f64)
-            gu = rho * (s_xh.t() @ w + s_hh @ u - ah[q])
-            th = self._exit_theta(rho * (gu * (s_hh @ gu)).sum() / (gu * gu).sum(), 1.0)
-            self.thetas["U" + gname] = th
-            thf = th.float()
-            self._wh[q].copy_((thf * self._wh[q] - gu.float()) / (float(hp.lam_u) + thf))
+        l_weight_phase(self._sxx, ax.view(5, D, H), ah.view(5, H, H), stt.view(H, H), pt, self._wx, self._wh, self._wy,
+                       rho_s=float(hp.rho_s), rho11=float(hp.rho11), lam_w=float(hp.lam_w), lam_u=float(hp.lam_u),
+                       thetas=self.thetas)
         if self._tc_ws is not None:
             self._call("admm_tc_refresh", self._bp, _lib.TC_WEIGHTS, st)
 
         # ---- theta of update_h at t = T-1 (:251-257): Func2 > Func1  <=>  theta < rho11 ||Wy||^2
         wy = self._wy.to(f64)
-        th = self._exit_theta(float(hp.rho11) * (wy @ wy), 1.0)
+        th = exit_theta(float(hp.rho11) * (wy @ wy), 1.0)
         self.thetas["h"] = th
         self._theta_h.copy_(th.float().reshape(1))
 

@@ -38,7 +38,6 @@ struct LSlot {
   float* lam9;
   float* lam10;
   const float* P;        // [4][H][ldn] = x W + h_{s-1} U
-  float* h_lo;           // tf32 low part of h at slot s, or nullptr
   __half* h16_hi;        // fp16 pair of h 2^11 at slot s (the gate GEMM's A operand), or nullptr
   __half* h16_lo;
   unsigned* bound_track; // tensor-core path: running max of |z_g + lambda_s,g/rho_s| and |h| (bit pattern): the bound
@@ -47,8 +46,7 @@ struct LSlot {
 };
 
 __device__ __forceinline__ void l_store_h_side(const LSlot& p, int64_t idx, float h) {
-  if (!p.h_lo) return;
-  p.h_lo[idx] = tf32_lo(h);
+  if (!p.h16_hi) return;
   const float c = fminf(fmaxf(h * 2048.0f, -65504.0f), 65504.0f);       // 2^11 = SCALE_H of gate_gemm_tc.cu
   const __half hh = __float2half_rn(c);
   p.h16_hi[idx] = hh;
@@ -400,10 +398,9 @@ LSlot make_slot(const admm_l_problem* lp, int s, const float* P) {
   k.lam9 = lp->lam9 + (int64_t)s * slab;
   k.lam10 = lp->lam10 + (int64_t)s * slab;
   k.P = P;
-  k.h_lo = nullptr; k.h16_hi = k.h16_lo = nullptr; k.bound_track = nullptr;
+  k.h16_hi = k.h16_lo = nullptr; k.bound_track = nullptr;
   if (b.tc_ws && tc_eligible(&b)) {
     k.bound_track = tc_r_bound(&b);
-    k.h_lo = tc_h_lo(&b) + (int64_t)s * slab;
     tc_h16(&b, &k.h16_hi, &k.h16_lo);
     k.h16_hi += (int64_t)s * slab;
     k.h16_lo += (int64_t)s * slab;
@@ -481,15 +478,15 @@ int admm_l_sums(const admm_l_problem* lp, int t0, int tc, float* scratch, double
   AtrArgs r;
   memset(&r, 0, sizeof(r));
   r.ldn = b.ldn; r.H = b.H; r.tc = tc; r.rows = 5 * b.H; r.rpg = b.H;
-  r.scratch = scratch; r.scratch_lo = use_tc ? scratch + half : nullptr;
+  r.scratch = scratch; r.scratch_lo = nullptr;            // without fp16 pairs: the fp32 CUDA-core reduction
   if (f16) { r.r16_hi = k.r16_hi; r.r16_lo = k.r16_lo; r.r_bound = k.r_bound; }
   // src = x: P_x[g] and S_xh
   r.K = b.D; r.a_src = b.x + (int64_t)t0 * b.D * b.ldn; r.a_tstride = (int64_t)b.D * b.ldn; r.g_acc = acc_x;
-  rc = use_tc ? atr_tc(&b, r, st) : atr_simt(r, st);
+  rc = f16 ? atr_tc(&b, r, st) : atr_simt(r, st);
   if (rc) return rc;
   // src = h_{t-1}: P_h[g] and S_hh
   r.K = b.H; r.a_src = b.gate[5] + (int64_t)t0 * b.H * b.ldn; r.a_tstride = (int64_t)b.H * b.ldn; r.g_acc = acc_h;
-  return use_tc ? atr_tc(&b, r, st) : atr_simt(r, st);
+  return f16 ? atr_tc(&b, r, st) : atr_simt(r, st);
 }
 
 int admm_l_gram_xx(const admm_l_problem* lp, double* sxx, void* stream) {
@@ -516,14 +513,13 @@ int admm_l_sums_last(const admm_l_problem* lp, double* s_tt, double* p_t, void* 
   ADMM_REQUIRE(s_tt && p_t, "admm_l_sums_last: null buffers");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t slab = (int64_t)b.H * b.ldn;
-  const bool use_tc = b.tc_ws && tc_eligible(&b);
   AtrArgs r;
   memset(&r, 0, sizeof(r));
   r.ldn = b.ldn; r.H = b.H; r.tc = 1; r.rows = b.H; r.rpg = b.H;
   r.K = b.H; r.a_src = b.gate[5] + (int64_t)b.T * slab; r.a_tstride = slab;
-  r.scratch = r.a_src; r.scratch_lo = use_tc ? tc_h_lo(&b) + (int64_t)b.T * slab : nullptr;
+  r.scratch = r.a_src; r.scratch_lo = nullptr;
   r.g_acc = s_tt;
-  rc = use_tc ? atr_tc(&b, r, st) : atr_simt(r, st);
+  rc = atr_simt(r, st);                 // one [H,H] Gram of a single timestep: CUDA-core reduction
   if (rc) return rc;
   l_pt_kernel<<<b.H, NT, 0, st>>>(b.gate[5] + (int64_t)b.T * slab, b.a, b.dual_y, lp->hp.rho11, b.n, b.ldn, p_t);
   count_launch();

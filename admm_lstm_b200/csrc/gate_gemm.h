@@ -38,7 +38,6 @@ struct GateGemmArgs {
   float* zstore;         // [4][H][zT][ldn] pre-activation store (tensor-core path) or nullptr
   int32_t zT, zt0;       // zstore timesteps, first timestep (0-based) of this launch
   int32_t z_accumulate;  // GRAD: z = zstore + acc (acc = x (W_new - W_old)) instead of z = acc
-  float* h_lo;           // slab t of the h - tf32(h) side buffer (tensor-core path) or nullptr
   __half* h16_hi;        // slab t of the fp16 pair of h 2^11 (tensor-core path): the gate GEMM's A operand
   __half* h16_lo;
   const float* acc_scale;  // tensor-core path: 2^-(sa+sb) that turns the accumulator of this launch into z or Q

@@ -200,7 +200,6 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
 #pragma unroll
         for (int q = 0; q < 6; ++q)
           if (p.gate[q]) st_stream(p.gate[q] + off, make_float4(o_[q][0], o_[q][1], o_[q][2], o_[q][3]));
-        if (p.h_lo) st_stream(p.h_lo + off, make_float4(tf32_lo(o_[5][0]), tf32_lo(o_[5][1]), tf32_lo(o_[5][2]), tf32_lo(o_[5][3])));
       }
 
       if (MODE == GG_RAWZ) {
@@ -247,7 +246,6 @@ gate_gemm_simt_kernel(const GateGemmArgs p) {
           st_stream(p.gate[q] + off, make_float4(out_[q][0], out_[q][1], out_[q][2], out_[q][3]));
         if (!p.last) {
           st_stream(p.gate[5] + off, make_float4(out_[5][0], out_[5][1], out_[5][2], out_[5][3]));
-          if (p.h_lo) st_stream(p.h_lo + off, make_float4(tf32_lo(out_[5][0]), tf32_lo(out_[5][1]), tf32_lo(out_[5][2]), tf32_lo(out_[5][3])));
         }
 #pragma unroll
         for (int q = 0; q < 5; ++q)

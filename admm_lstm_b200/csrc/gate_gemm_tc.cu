@@ -230,7 +230,6 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             if (p.gate[3]) __stcs(p.gate[3] + off[e], r.o);
             __stcs(p.gate[4] + off[e], r.c);
             p.gate[5][off[e]] = r.h;
-            if (p.h_lo) p.h_lo[off[e]] = tf32_lo(r.h);       // tf32 pair of the A^T R reduction GEMM
             store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h);   // fp16 pair: the next timestep's A operand
           }
         }
@@ -273,7 +272,6 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             p.gate[4][off[e]] = r.c;                         // c_t is read again by the next timestep
             if (!p.last) {
               p.gate[5][off[e]] = r.h;
-              if (p.h_lo) p.h_lo[off[e]] = tf32_lo(r.h);
               store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h);
             }
             __stcs(p.dual[0] + off[e], r.li); __stcs(p.dual[1] + off[e], r.lf); __stcs(p.dual[2] + off[e], r.lg);
@@ -546,9 +544,9 @@ struct TcMeta {
 };
 
 // workspace layout in floats (fp16 buffers take half a float per element):
-// [x_lo][h_lo] tf32 low parts for the A^T R GEMM | fp16 pairs of x, h, wx, wh, g | TcMeta
+// [x_lo] tf32 low part of x for the x-phase A^T R GEMM | fp16 pairs of x, h, wx, wh, g | TcMeta
 struct WsLayout {
-  int64_t x_lo, h_lo, x16_hi, x16_lo, h16_hi, h16_lo, wx_hi, wx_lo, wh_hi, wh_lo, g_hi, g_lo, meta, total;
+  int64_t x_lo, x16_hi, x16_lo, h16_hi, h16_lo, wx_hi, wx_lo, wh_hi, wh_lo, g_hi, g_lo, meta, total;
 };
 WsLayout ws_layout(const admm_problem* p) {
   WsLayout w;
@@ -558,7 +556,6 @@ WsLayout ws_layout(const admm_problem* p) {
   auto take = [&](int64_t n) { const int64_t r = o; o += (n + 255) / 256 * 256; return r; };
   auto take16 = [&](int64_t n) { return take((n + 1) / 2); };
   w.x_lo = take(T * D * ldn);
-  w.h_lo = take((T + 1) * H * ldn);
   w.x16_hi = take16(T * D * ldn); w.x16_lo = take16(T * D * ldn);
   w.h16_hi = take16((T + 1) * H * ldn); w.h16_lo = take16((T + 1) * H * ldn);
   w.wx_hi = take16(4 * D * H); w.wx_lo = take16(4 * D * H);
@@ -747,10 +744,7 @@ int tc_refresh_inputs(const admm_problem* p, cudaStream_t st) {
 
 int tc_refresh_state(const admm_problem* p, cudaStream_t st) {
   const WsLayout w = ws_layout(p);
-  float* ws = (float*)p->tc_ws;
   const int64_t nh = (int64_t)(p->T + 1) * p->H * p->ldn;
-  split_trunc_kernel<<<(unsigned)((nh / 4 + 255) / 256 + 1), 256, 0, st>>>(p->gate[5], ws + w.h_lo, nh);
-  count_launch();
   return prep_operand(PREP_H, p->gate[5], nullptr, ws_half(p, w.h16_hi), ws_half(p, w.h16_lo), nh, ws_meta(p), nullptr, st);
 }
 
@@ -778,10 +772,6 @@ void tc_h16(const admm_problem* p, __half** hi, __half** lo) {
   *lo = ws_half(p, w.h16_lo);
 }
 
-float* tc_h_lo(const admm_problem* p) {
-  return (float*)p->tc_ws + ws_layout(p).h_lo;
-}
-
 int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int tc, cudaStream_t st) {
   GateGemmArgs a = a_in;
   TcMaps maps;
@@ -792,7 +782,6 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   // slab index of h_{t-1} / x_t of the first timestep in the launch
   const int64_t slab_elems = (int64_t)p->H * p->ldn;
   const int slab0 = (int)((a.h_prev - p->gate[5]) / slab_elems);
-  a.h_lo = tc_h_lo(p) + (a.gate[5] - p->gate[5]);
   {
     __half *hi, *lo;
     tc_h16(p, &hi, &lo);
@@ -1005,7 +994,7 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
                        ldn, D * ldn, BKN, NT_, 1, F16);
   } else {
     rc |= make_map_box(&m.h, F16 ? (const void*)ws_half(p, w.h16_hi) : (const void*)p->gate[5], ldn, H, T1, ldn, H * ldn, BKN, NT_, 1, F16);
-    rc |= make_map_box(&m.h_lo, F16 ? (const void*)ws_half(p, w.h16_lo) : (const void*)tc_h_lo(p), ldn, H, T1, ldn, H * ldn, BKN,
+    rc |= make_map_box(&m.h_lo, F16 ? (const void*)ws_half(p, w.h16_lo) : (const void*)nullptr, ldn, H, T1, ldn, H * ldn, BKN,
                        NT_, 1, F16);
   }
   if (rc) return ADMM_ECUDA;
@@ -1043,6 +1032,7 @@ int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st) {
     if (a.K > 64) return launch_atr_any<128>(p, a, slab0, true, st);
     return launch_atr_any<64>(p, a, slab0, true, st);
   }
+  if (!a.r16_hi) return atr_simt(a, st);       // A_src = h exists on the tensor-core path only as fp16 pairs
   const int slab0 = (int)((a.a_src - p->gate[5]) / ((int64_t)p->H * p->ldn));
   if (p->H >= 256) return launch_atr_any<256>(p, a, slab0, false, st);
   if (p->H >= 128) return launch_atr_any<128>(p, a, slab0, false, st);

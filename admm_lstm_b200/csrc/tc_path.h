@@ -15,7 +15,6 @@ int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStrea
 int tc_refresh_wx_delta(const admm_problem* p, cudaStream_t st);
 int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st);
 int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st);
-float* tc_h_lo(const admm_problem* p);
 unsigned* tc_r_bound(const admm_problem* p);     // device slot: bound on |R| of the fp16 A^T R operand (bit pattern)
 void tc_h16(const admm_problem* p, __half** hi, __half** lo);   // fp16 pair of h 2^11, [T+1][H][ldn] each
 

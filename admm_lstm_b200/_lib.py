@@ -90,15 +90,14 @@ SIGNATURES = {
     "admm_launch_count": (C.c_int64, [C.c_int]),
     # ADMM-LSTM-L
     "admm_l_sizeof_problem": (C.c_int, []),
-    "admm_l_forward_t": (C.c_int, [LPP, C.c_int, vp, vp]),
+    "admm_l_forward_t": (C.c_int, [LPP, C.c_int, vp, vp, vp]),
     "admm_l_output": (C.c_int, [LPP, vp]),
     "admm_l_sums": (C.c_int, [LPP, C.c_int, C.c_int, vp, vp, vp, vp]),
     "admm_l_gram_xx": (C.c_int, [LPP, vp, vp]),
     "admm_l_sums_last": (C.c_int, [LPP, vp, vp, vp]),
-    "admm_l_sweep_max": (C.c_int, [LPP, C.c_int, vp, vp, vp]),
     "admm_l_sweep_gates": (C.c_int, [LPP, C.c_int, vp, vp, vp, vp]),
-    "admm_l_sweep_cell": (C.c_int, [LPP, C.c_int, vp, vp, vp, vp]),
-    "admm_l_last": (C.c_int, [LPP, vp, vp, vp, vp]),
+    "admm_l_sweep_cell": (C.c_int, [LPP, C.c_int, vp, vp, vp, vp, vp]),
+    "admm_l_last": (C.c_int, [LPP, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -157,7 +157,10 @@ class ADMMLOptimizer(object):
         self._tc_chunk = max(1, min(T, budget // (40 * H * ldn)))
         self._scratch = torch.empty(max(10 * H * self._tc_chunk * ldn, 4 * H * ldn), dtype=f32, device=dev)
         self._tmp = torch.empty(ldn, dtype=f32, device=dev)
-        self._red_max = torch.zeros((T + 1, 8), dtype=f32, device=dev)
+        # per slot: [0..3] max |gate - lambda_p/rho| (measured when the values are written, one iteration ahead),
+        # [4] the mid-timestep max of update_c; two buffers: this iteration's and the next one's
+        self._red_max = [torch.zeros((T + 1, 8), dtype=f32, device=dev) for _ in range(2)]
+        self._red_cur = 0
         self._red_sum = torch.zeros(T + 1, dtype=f64, device=dev)
         # [acc_x (5*D*H) | acc_h (5*H*H) | s_tt (H*H) | p_t (H)]: one all-reduce per iteration
         self._n_ax, self._n_ah = 5 * D * H, 5 * H * H
@@ -198,7 +201,7 @@ class ADMMLOptimizer(object):
 
         st = _stream_ptr()
         for s in range(1, T + 1):                                            # main.py:105 LSTM_Forward(train_x)
-            self._call("admm_l_forward_t", self._lpp, s, self._scratch.data_ptr(), st)
+            self._call("admm_l_forward_t", self._lpp, s, self._scratch.data_ptr(), self._red_max[0][s].data_ptr(), st)
         self._call("admm_l_output", self._lpp, st)
         self._call("admm_l_gram_xx", self._lpp, self._sxx.data_ptr(), st)
         self.comm.allreduce_sum_(self._sxx)
@@ -277,18 +280,19 @@ class ADMMLOptimizer(object):
         self._theta_h.copy_(th.float().reshape(1))
 
         # ---- sweep (main.py:149-188)
-        self._red_max.zero_()
+        cur, nxt = self._red_max[self._red_cur], self._red_max[1 - self._red_cur]
+        self.comm.allreduce_max_(cur)                      # the T x 4 gate maxima of this iteration in one collective
+        nxt.zero_()
         self._red_sum.zero_()
         sp = self._scratch.data_ptr()
         for s in range(1, T + 1):
-            rm, rs = self._red_max[s], self._red_sum[s:s + 1]
-            self._call("admm_l_sweep_max", lpp, s, sp, rm.data_ptr(), st)
-            self.comm.allreduce_max_(rm)
+            rm, rs = cur[s], self._red_sum[s:s + 1]
             self._call("admm_l_sweep_gates", lpp, s, sp, rm.data_ptr(), rs.data_ptr(), st)
-            self.comm.allreduce_max_(rm)
+            self.comm.allreduce_max_(rm[4:5])
             self.comm.allreduce_sum_(rs)
-            self._call("admm_l_sweep_cell", lpp, s, sp, rm.data_ptr(), rs.data_ptr(), st)
-        self._call("admm_l_last", lpp, self._theta_h.data_ptr(), self._tmp.data_ptr(), sp, st)
+            self._call("admm_l_sweep_cell", lpp, s, sp, rm.data_ptr(), rs.data_ptr(), nxt[s].data_ptr(), st)
+        self._call("admm_l_last", lpp, self._theta_h.data_ptr(), self._tmp.data_ptr(), sp, nxt[T].data_ptr(), st)
+        self._red_cur = 1 - self._red_cur
 
     # ------------------------------------------------------------------------------------------ observables
     def weights(self) -> Dict[str, torch.Tensor]:

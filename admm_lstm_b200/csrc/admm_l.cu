@@ -40,6 +40,9 @@ struct LSlot {
   const float* P;        // [4][H][ldn] = x W + h_{s-1} U
   __half* h16_hi;        // fp16 pair of h 2^11 at slot s (the gate GEMM's A operand), or nullptr
   __half* h16_lo;
+  float* next_max;       // [4]: max |gate_g - lambda_p,g/rho_p| of the values this iteration leaves at slot s, i.e. the
+                         // torch.max of update_z / update_zg (admm_lstm.py:168,179) of the NEXT iteration -- measured when
+                         // the values are written instead of by a separate pass over the state
   unsigned* bound_track; // tensor-core path: running max of |z_g + lambda_s,g/rho_s| and |h| (bit pattern): the bound
                          // that scales the fp16 operand of the next iteration's Gram / right-hand-side pass
   admm_l_hyper hp;
@@ -58,6 +61,12 @@ __device__ __forceinline__ void track_bound(unsigned* slot, float b) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
   if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(b));
+}
+
+__device__ __forceinline__ void track_max(float* slot, float b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(b));
 }
 
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -80,6 +89,7 @@ __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
 __global__ void __launch_bounds__(NT) l_forward_kernel(const LSlot p) {
   const int64_t total = (int64_t)p.H * p.ldn;
   float bmax = 0.f;
+  float gmax[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
     const int64_t n = idx % p.ldn;
     if (n >= p.n) continue;
@@ -97,8 +107,12 @@ __global__ void __launch_bounds__(NT) l_forward_kernel(const LSlot p) {
     p.gate[4][idx] = c; p.gate[5][idx] = h;
     l_store_h_side(p, idx, h);
     bmax = fmaxf(bmax, fabsf(h));
+    gmax[0] = fmaxf(gmax[0], fabsf(i)); gmax[1] = fmaxf(gmax[1], fabsf(f));       // lambda_p = 0 at the start
+    gmax[2] = fmaxf(gmax[2], fabsf(gg)); gmax[3] = fmaxf(gmax[3], fabsf(o));
   }
   track_bound(p.bound_track, bmax);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) track_max(p.next_max + q, gmax[q]);
 }
 
 // ---------------------------------------------------------------------------------------------------- packing
@@ -175,23 +189,6 @@ __global__ void __launch_bounds__(NT) l_pt_kernel(const float* hT, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------------- sweep
-// red_max[g] = max |gate_g - lambda_p,g / rho_p|          (admm_lstm.py:168, 179)
-__global__ void __launch_bounds__(NT) l_max_kernel(const LSlot p, float* red_max) {
-  __shared__ float red[NT / 32];
-  const int64_t total = (int64_t)p.H * p.ldn;
-  float m[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    if (idx % p.ldn >= p.n) continue;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) m[g] = fmaxf(m[g], fabsf(p.gate[g][idx] - p.lam_p[g][idx] / p.hp.rho_p));
-  }
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float b = block_max(m[g], red);
-    if (threadIdx.x == 0) atomic_max_nonneg(red_max + g, b);
-  }
-}
-
 // update_z / update_zg (admm_lstm.py:166-188)
 __device__ __forceinline__ float l_update_z(float z, float out, float P, float lam1, float lam2, float rs, float rp,
                                             float appro, bool is_g) {
@@ -265,7 +262,8 @@ __device__ __forceinline__ LDualIn l_duals_load(const LSlot& p, int64_t idx, int
   }
   return d;
 }
-__device__ __forceinline__ float l_duals_store(const LSlot& p, int64_t idx, const LDualIn& d, float c, float h, float c_) {
+__device__ __forceinline__ void l_duals_store(const LSlot& p, int64_t idx, const LDualIn& d, float c, float h, float c_,
+                                              float (&acc)[5]) {     // acc[0..3]: next iteration's maxima, acc[4]: |V|, |h| bound
   const float rs = p.hp.rho_s, rp = p.hp.rho_p, r9 = p.hp.rho9, r10 = p.hp.rho10;
   const float n10 = d.l10 + r10 * (tanhf(c) * d.o - h);
   const float n9 = d.l9 + r9 * (c - d.g * d.i - c_ * d.f);
@@ -278,12 +276,13 @@ __device__ __forceinline__ float l_duals_store(const LSlot& p, int64_t idx, cons
     np_[q] = d.lp[q] + rp * (act - gv[q]);
     ns_[q] = d.ls[q] + rs * (d.z[q] - d.P[q]);
     b = fmaxf(b, fabsf(d.z[q] + ns_[q] / rs));          // |V| of the next packing pass (l_pack_kernel)
+    acc[q] = fmaxf(acc[q], fabsf(gv[q] - np_[q] / rp));  // admm_lstm.py:168,179 of the next iteration
   }
   p.lam10[idx] = n10;
   p.lam9[idx] = n9;
 #pragma unroll
   for (int q = 0; q < 4; ++q) { p.lam_p[q][idx] = np_[q]; p.lam_s[q][idx] = ns_[q]; }
-  return b;
+  acc[4] = fmaxf(acc[4], b);
 }
 
 // update_c (:223-241), update_h for s < T (:249-250), then the duals.  LAST: c only.
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* 
   const float r9 = p.hp.rho9, r10 = p.hp.rho10;
   const float appro_h = appro_tanh(red_max[4]);
   const float qua_o = (float)red_sum[0];
-  float bmax = 0.f;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
     if (idx % p.ldn >= p.n) continue;
     const LDualIn d = l_duals_load(p, idx, total);
@@ -312,10 +311,14 @@ __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* 
       p.gate[4][idx] = c;
       p.gate[5][idx] = hn;
       l_store_h_side(p, idx, hn);
-      bmax = fmaxf(bmax, l_duals_store(p, idx, d, c, hn, c_));
+      l_duals_store(p, idx, d, c, hn, c_, acc);
     }
   }
-  if (!LAST) track_bound(p.bound_track, bmax);
+  if (!LAST) {
+    track_bound(p.bound_track, acc[4]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) track_max(p.next_max + q, acc[q]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------- t = T-1
@@ -357,13 +360,15 @@ __global__ void __launch_bounds__(NT) l_last_a_kernel(const float* h, const floa
 }
 __global__ void __launch_bounds__(NT) l_duals_kernel(const LSlot p) {
   const int64_t total = (int64_t)p.H * p.ldn;
-  float bmax = 0.f;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
     if (idx % p.ldn >= p.n) continue;
     const LDualIn d = l_duals_load(p, idx, total);
-    bmax = fmaxf(bmax, l_duals_store(p, idx, d, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx]));
+    l_duals_store(p, idx, d, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx], acc);
   }
-  track_bound(p.bound_track, bmax);
+  track_bound(p.bound_track, acc[4]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) track_max(p.next_max + q, acc[q]);
 }
 
 // ---------------------------------------------------------------------------------------------------- host helpers
@@ -383,7 +388,7 @@ int validate_l(const admm_l_problem* lp, const char* who) {
   return ADMM_OK;
 }
 
-LSlot make_slot(const admm_l_problem* lp, int s, const float* P) {
+LSlot make_slot(const admm_l_problem* lp, int s, const float* P, float* next_max = nullptr) {
   LSlot k;
   const admm_problem& b = lp->base;
   const int64_t slab = (int64_t)b.H * b.ldn;
@@ -398,6 +403,7 @@ LSlot make_slot(const admm_l_problem* lp, int s, const float* P) {
   k.lam9 = lp->lam9 + (int64_t)s * slab;
   k.lam10 = lp->lam10 + (int64_t)s * slab;
   k.P = P;
+  k.next_max = next_max;
   k.h16_hi = k.h16_lo = nullptr; k.bound_track = nullptr;
   if (b.tc_ws && tc_eligible(&b)) {
     k.bound_track = tc_r_bound(&b);
@@ -431,14 +437,14 @@ extern "C" {
 
 int admm_l_sizeof_problem(void) { return (int)sizeof(admm_l_problem); }
 
-int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, void* stream) {
+int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, float* next_max, void* stream) {
   int rc = validate_l(lp, "admm_l_forward_t");
   if (rc) return rc;
-  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch, "admm_l_forward_t: bad arguments");
+  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && next_max, "admm_l_forward_t: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (s == 1 && (rc = reset_bound(lp, st))) return rc;
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
-  const LSlot k = make_slot(lp, s, scratch);
+  const LSlot k = make_slot(lp, s, scratch, next_max);
   l_forward_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k);
   count_launch();
   return check_launch("l_forward");
@@ -526,35 +532,25 @@ int admm_l_sums_last(const admm_l_problem* lp, double* s_tt, double* p_t, void* 
   return check_launch("l_pt");
 }
 
-int admm_l_sweep_max(const admm_l_problem* lp, int s, float* scratch, float* red_max, void* stream) {
-  int rc = validate_l(lp, "admm_l_sweep_max");
+int admm_l_sweep_gates(const admm_l_problem* lp, int s, float* scratch, float* red_max, double* red_sum, void* stream) {
+  int rc = validate_l(lp, "admm_l_sweep_gates");
   if (rc) return rc;
-  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max, "admm_l_sweep_max: bad arguments");
+  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum, "admm_l_sweep_gates: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (s == 1 && (rc = reset_bound(lp, st))) return rc;       // the sweep re-measures the bound of the next packing pass
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch);
-  l_max_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k, red_max);
-  count_launch();
-  return check_launch("l_max");
-}
-
-int admm_l_sweep_gates(const admm_l_problem* lp, int s, const float* scratch, float* red_max, double* red_sum, void* stream) {
-  int rc = validate_l(lp, "admm_l_sweep_gates");
-  if (rc) return rc;
-  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum, "admm_l_sweep_gates: bad arguments");
-  const LSlot k = make_slot(lp, s, scratch);
-  l_gates_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
+  l_gates_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k, red_max, red_sum);
   count_launch();
   return check_launch("l_gates");
 }
 
 int admm_l_sweep_cell(const admm_l_problem* lp, int s, const float* scratch, const float* red_max, const double* red_sum,
-                      void* stream) {
+                      float* next_max, void* stream) {
   int rc = validate_l(lp, "admm_l_sweep_cell");
   if (rc) return rc;
-  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum, "admm_l_sweep_cell: bad arguments");
-  const LSlot k = make_slot(lp, s, scratch);
+  ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum && next_max, "admm_l_sweep_cell: bad arguments");
+  const LSlot k = make_slot(lp, s, scratch, next_max);
   const unsigned grid = ew_grid((int64_t)k.H * k.ldn);
   if (s == lp->base.T) l_cell_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
   else l_cell_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
@@ -562,13 +558,14 @@ int admm_l_sweep_cell(const admm_l_problem* lp, int s, const float* scratch, con
   return check_launch("l_cell");
 }
 
-int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, const float* scratch, void* stream) {
+int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, const float* scratch, float* next_max,
+                void* stream) {
   int rc = validate_l(lp, "admm_l_last");
   if (rc) return rc;
-  ADMM_REQUIRE(theta_h && tmp && scratch, "admm_l_last: null buffers");
+  ADMM_REQUIRE(theta_h && tmp && scratch && next_max, "admm_l_last: null buffers");
   const admm_problem& b = lp->base;
   cudaStream_t st = (cudaStream_t)stream;
-  const LSlot k = make_slot(lp, b.T, scratch);
+  const LSlot k = make_slot(lp, b.T, scratch, next_max);
   const unsigned nb = (unsigned)((b.n + NT - 1) / NT);
   const unsigned grid = ew_grid((int64_t)k.H * k.ldn);
   l_form10_kernel<<<nb, NT, 0, st>>>(k.gate[5], b.wy, b.a, b.dual_y, lp->hp.rho11, b.n, b.ldn, b.H, tmp);

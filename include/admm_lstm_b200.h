@@ -231,8 +231,10 @@ typedef struct admm_l_problem {
 
 int admm_l_sizeof_problem(void);
 
-/* main.py:85-103 at slot s = 1..T: z, gates, c, h (and the tensor-core side buffer of h).  scratch: 4*H*ldn floats. */
-int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, void* stream);
+/* main.py:85-103 at slot s = 1..T: z, gates, c, h (and the tensor-core side buffers of h); next_max[0..3] (zeroed by the
+ * caller) receives max |gate_g| of the slot, the torch.max of update_z / update_zg in the first iteration.
+ * scratch: 4*H*ldn floats. */
+int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, float* next_max, void* stream);
 /* a = h_T W_y (main.py:102) */
 int admm_l_output(const admm_l_problem* lp, void* stream);
 
@@ -248,23 +250,25 @@ int admm_l_sums(const admm_l_problem* lp, int t0, int tc, float* scratch, double
 int admm_l_gram_xx(const admm_l_problem* lp, double* sxx, void* stream);
 int admm_l_sums_last(const admm_l_problem* lp, double* s_tt, double* p_t, void* stream);
 
-/* The sweep at slot s (main.py:149-188) in three launches separated by the algorithm's own global reductions:
- *  max   : P = x W + h_{s-1} U for the four gates (gate GEMM -> scratch, 4*H*ldn floats) and
- *          red_max[g] = max |gate_g - lambda_p,g / rho_p|  (update_z/update_zg, :168,:179), g = i,f,g,o
- *  gates : z_f,f, z_i,i, z_o,o, z_g,g in the reference's Gauss-Seidel order (:166-220);
- *          red_max[4] = max |(h - lambda10/rho10)/o|, red_sum[0] = sum o^2  (update_c, :225,:230)
+/* The sweep at slot s (main.py:149-188): two elementwise kernels around the algorithm's mid-timestep reductions.
+ *  gates : P = x W + h_{s-1} U for the four gates (gate GEMM -> scratch, 4*H*ldn floats); z_f,f, z_i,i, z_o,o, z_g,g in the
+ *          reference's Gauss-Seidel order (:166-220) with red_max[g] = max |gate_g - lambda_p,g/rho_p| (update_z /
+ *          update_zg, :168,:179; g = i,f,g,o) as INPUT; writes red_max[4] = max |(h - lambda10/rho10)/o| and
+ *          red_sum[0] = sum o^2 (update_c, :225,:230)
  *  cell  : c (:223-241), h for s < T (:249-250) and the ten dual updates (:274-311); for s == T only c is written and
- *          admm_l_last() finishes the timestep.
- * red_max: 8 floats (non-negative, combined with MAX across shards), red_sum: 1 double (SUM); both zeroed by the
- * caller before `max`. */
-int admm_l_sweep_max(const admm_l_problem* lp, int s, float* scratch, float* red_max, void* stream);
-int admm_l_sweep_gates(const admm_l_problem* lp, int s, const float* scratch, float* red_max, double* red_sum, void* stream);
+ *          admm_l_last() finishes the timestep.  next_max[0..3] receives max |gate_g - lambda_p,g/rho_p| of the values
+ *          just written, i.e. the red_max[0..3] of slot s in the NEXT iteration (the reference's torch.max reads exactly
+ *          these values before it updates them), so no separate pass over the state is needed.
+ * red_max: 8 floats per slot (non-negative, combined with MAX across shards), red_sum: 1 double (SUM);
+ * red_max[4..7], red_sum and next_max zeroed by the caller. */
+int admm_l_sweep_gates(const admm_l_problem* lp, int s, float* scratch, float* red_max, double* red_sum, void* stream);
 int admm_l_sweep_cell(const admm_l_problem* lp, int s, const float* scratch, const float* red_max, const double* red_sum,
-                      void* stream);
+                      float* next_max, void* stream);
 /* s == T: h_T with theta_h[0] (update_h :251-258; the loop's exit is theta = smallest power of two >= max(1,
- * rho11 ||W_y||^2)), a (:262-266), lambda11 (:269-272), then the duals of slot T.  tmp: ldn floats;
- * scratch still holds P of slot T. */
-int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, const float* scratch, void* stream);
+ * rho11 ||W_y||^2)), a (:262-266), lambda11 (:269-272), then the duals of slot T (next_max as above).
+ * tmp: ldn floats; scratch still holds P of slot T. */
+int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, const float* scratch, float* next_max,
+                void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ ADMM_MAX_O = 16
 ADMM_MAX_CAND = 32
 ADMM_N_METRICS = 8
 ADMM_EST_CAND = 64
-ADMM_FK_SLOTS = 65
+ADMM_FK_SLOTS = 72
 VARIANT_ADMM, VARIANT_NO_DUAL_Y = 0, 1
 SRC_X, SRC_H = 0, 1
 TC_WEIGHTS, TC_INPUTS, TC_STATE = 1, 2, 4
@@ -44,7 +44,8 @@ class Problem(C.Structure):
 
 
 class ProbePlan(C.Structure):
-    _fields_ = [("k0", C.c_int32 * 4), ("ncand", C.c_int32), ("proof", C.c_int32)]
+    _fields_ = [("k0", C.c_int32 * 4), ("ncand", C.c_int32), ("proof", C.c_int32), ("moments", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 class LHyper(C.Structure):
@@ -77,8 +78,8 @@ SIGNATURES = {
     "admm_weight_begin": (C.c_int, [PP, C.c_int, vp]),
     "admm_weight_grad": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "admm_weight_finish_grad": (C.c_int, [PP, C.c_int, vp, vp, vp, vp]),
-    "admm_weight_probe": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, PLAN, vp, vp, vp]),
-    "admm_weight_select": (C.c_int, [PP, C.c_int, vp, vp, PLAN, C.c_int, vp, vp, vp]),
+    "admm_weight_probe": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, vp, PLAN, vp, vp, vp, vp]),
+    "admm_weight_select": (C.c_int, [PP, C.c_int, vp, vp, vp, PLAN, C.c_int, vp, vp, vp]),
     "admm_weight_apply": (C.c_int, [PP, C.c_int, vp, vp, vp]),
     "admm_sweep_t": (C.c_int, [PP, C.c_int, vp, vp]),
     "admm_last_probe": (C.c_int, [PP, vp, vp]),

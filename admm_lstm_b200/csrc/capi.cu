@@ -237,22 +237,24 @@ int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc,
 
 static int check_plan(const admm_probe_plan* plan, const char* who) {
   ADMM_REQUIRE(plan, "%s: null plan", who);
-  ADMM_REQUIRE(plan->ncand >= 1 && plan->ncand <= ADMM_MAX_CAND, "%s: bad ncand %d", who, plan->ncand);
+  ADMM_REQUIRE(plan->moments || (plan->ncand >= 1 && plan->ncand <= ADMM_MAX_CAND), "%s: bad ncand %d", who, plan->ncand);
   for (int g = 0; g < 4; ++g) {
-    ADMM_REQUIRE(plan->k0[g] >= 0 && plan->k0[g] + plan->ncand <= ADMM_EST_CAND, "%s: bad k0[%d]=%d", who, g, plan->k0[g]);
+    ADMM_REQUIRE(plan->k0[g] >= 0 && plan->k0[g] + (plan->moments ? 0 : plan->ncand) <= ADMM_EST_CAND, "%s: bad k0[%d]=%d", who,
+                 g, plan->k0[g]);
     ADMM_REQUIRE(!plan->proof || plan->k0[g] <= ADMM_MAX_CAND, "%s: proof range too long", who);
   }
   return ADMM_OK;
 }
 
 int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scratch, const float* grad,
-                      const admm_probe_plan* plan, const int32_t* done, double* fk_acc, void* stream) {
+                      const admm_probe_plan* plan, const int32_t* done, double* fk_acc, float* qmax, void* stream) {
   int rc = validate(p, "admm_weight_probe");
   if (rc) return rc;
   ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_probe: bad src");
   ADMM_REQUIRE(t0 >= 0 && tc >= 1 && t0 + tc <= p->T, "admm_weight_probe: bad timestep range");
   if ((rc = check_plan(plan, "admm_weight_probe"))) return rc;
   ADMM_REQUIRE(scratch && grad && done && fk_acc, "admm_weight_probe: null buffers");
+  ADMM_REQUIRE(!plan->moments || qmax, "admm_weight_probe: a moments plan needs qmax");
   cudaStream_t st = (cudaStream_t)stream;
   GateGemmArgs a = base_args(p, t0 + 1);
   const int64_t half = 4LL * p->H * tc * p->ldn;
@@ -272,7 +274,7 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
   // window: all units, theta = 2^(k0[g] + c)
   for (int g = 0; g < 4; ++g) { e.kbase[g] = plan->k0[g]; e.nc[g] = plan->ncand; e.slot0[g] = 0; }
   e.jmod = 1; e.jrem = 0; e.publish_fw = 1;
-  rc = probe_eval(e, st);
+  rc = plan->moments ? probe_moments(e, qmax, st) : probe_eval(e, st);
   if (rc || !plan->proof) return rc;
   // lower bounds below the window: every k < k0[g] on unit blocks 0 mod 8, and the three exponents next to the
   // window additionally on the odd blocks (disjoint sets, so the sums add up to one partial sum over 5/8 of the units)
@@ -289,14 +291,15 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
   return probe_eval(e, st);
 }
 
-int admm_weight_select(const admm_problem* p, int src, const double* est_acc, const double* fk_acc,
+int admm_weight_select(const admm_problem* p, int src, const double* est_acc, const double* fk_acc, const float* qmax,
                        const admm_probe_plan* plan, int final_pass, int32_t* done, float* theta_out, void* stream) {
   int rc = validate(p, "admm_weight_select");
   if (rc) return rc;
   (void)src;
   if ((rc = check_plan(plan, "admm_weight_select"))) return rc;
   ADMM_REQUIRE(est_acc && fk_acc && done && theta_out, "admm_weight_select: null buffers");
-  return launch_weight_select(*p, est_acc, fk_acc, *plan, final_pass, done, theta_out, (cudaStream_t)stream);
+  ADMM_REQUIRE(!plan->moments || qmax, "admm_weight_select: a moments plan needs qmax");
+  return launch_weight_select(*p, est_acc, fk_acc, qmax, *plan, final_pass, done, theta_out, (cudaStream_t)stream);
 }
 
 int admm_weight_apply(const admm_problem* p, int src, const float* grad, const float* theta, void* stream) {

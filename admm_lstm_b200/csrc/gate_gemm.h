@@ -93,6 +93,10 @@ struct ProbeEvalArgs {
   double* fk_acc;        // [4][ADMM_FK_SLOTS]
 };
 int probe_eval(const ProbeEvalArgs& a, cudaStream_t st);
+// Moment pass of a `moments` plan (admm_probe_plan): fk_acc[g][ADMM_FK_MOMENTS + 0..4] += F0, B1..B4 and
+// qmax[g] = max(qmax[g], max |Q|).  Uses z0, q, gate, dual, rho, done, kbase (= the plan's k0: normalisation 2^-k0 of Q)
+// and fk_acc of the same argument block.
+int probe_moments(const ProbeEvalArgs& a, float* qmax, cudaStream_t st);
 
 // x-phase gradient residual from stored pre-activations (grad_from_z.cu): R^T, its tf32 low part and f(w).
 struct GradFromZArgs {

@@ -322,14 +322,14 @@ __global__ void __launch_bounds__(256) weight_est_kernel(const float* w_all, con
 // Replays admm.py:331-338 per gate from the reduced sums: theta_k = 2^k, est_k = f(w) + s1_k + T*0.5*theta_k*s2_k, exit at
 // the first k with !(f(beta_k) > est_k).  With plan.proof the candidates below the window are represented by
 // lower bounds of f(beta_k): "bound > est_k" proves the loop continues; an unproven k leaves the gate undecided.
-__global__ void weight_select_kernel(const double* est_acc, const double* fk_acc, admm_hyper hp, int T,
+__global__ void weight_select_kernel(const double* est_acc, const double* fk_acc, const float* qmax, admm_hyper hp, int T,
                                      admm_probe_plan plan, int final_pass, int32_t* done, float* theta_out) {
   const int g = threadIdx.x;
   if (g >= 4 || done[g]) return;
   const float rho = hp.rho[g];
   const double* fk = fk_acc + g * ADMM_FK_SLOTS;
   const double* es = est_acc + (int64_t)g * ADMM_EST_CAND * 2;
-  const float f_w = 0.5f * rho * (float)fk[ADMM_MAX_CAND];
+  const float f_w = 0.5f * rho * (float)fk[plan.moments ? ADMM_FK_MOMENTS : ADMM_MAX_CAND];
   auto est = [&](int k) {
     const float theta = ldexpf(1.0f, k);
     return f_w + (float)es[2 * k] + ((float)T * 0.5f * theta) * (float)es[2 * k + 1];
@@ -343,6 +343,27 @@ __global__ void weight_select_kernel(const double* est_acc, const double* fk_acc
         return;
       }
     }
+  }
+  if (plan.moments) {
+    // f(w + G/2^k) = F0 + B1 x + B2 x^2 + B3 x^3 + B4 x^4, x = 2^-k, valid where max|Q| x <= 2^-5 (admm_probe_plan)
+    if (!(ldexpf(qmax[g], -k0) <= 0.03125f)) {
+      done[4 + g] = 3; done[8 + g] = k0;
+      return;
+    }
+    const double* m = fk + ADMM_FK_MOMENTS;
+    for (int k = k0; k < ADMM_EST_CAND; ++k) {
+      const double x = ldexp(1.0, -k);
+      const double f_k = m[0] + x * (m[1] + x * (m[2] + x * (m[3] + x * m[4])));
+      const float f_b = 0.5f * rho * (float)f_k;
+      if (!(f_b > est(k))) {
+        theta_out[g] = ldexpf(1.0f, k - 1);          // theta /= 2 (admm.py:338)
+        done[g] = 1;
+        return;
+      }
+    }
+    theta_out[g] = ldexpf(1.0f, ADMM_EST_CAND - 1);   // iteration cap (the reference has none)
+    done[g] = 1;
+    return;
   }
   int found = -1;
   for (int c = 0; c < plan.ncand; ++c) {
@@ -426,9 +447,9 @@ int launch_weight_est(const admm_problem& p, int src, const float* grad, double*
   count_launch();
   return check_launch("weight_est");
 }
-int launch_weight_select(const admm_problem& p, const double* est_acc, const double* fk_acc, const admm_probe_plan& plan,
-                         int final_pass, int32_t* done, float* theta, cudaStream_t st) {
-  weight_select_kernel<<<1, 32, 0, st>>>(est_acc, fk_acc, p.hp, p.T, plan, final_pass, done, theta);
+int launch_weight_select(const admm_problem& p, const double* est_acc, const double* fk_acc, const float* qmax,
+                         const admm_probe_plan& plan, int final_pass, int32_t* done, float* theta, cudaStream_t st) {
+  weight_select_kernel<<<1, 32, 0, st>>>(est_acc, fk_acc, qmax, p.hp, p.T, plan, final_pass, done, theta);
   count_launch();
   return check_launch("weight_select");
 }

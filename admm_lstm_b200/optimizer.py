@@ -15,6 +15,7 @@ the device, so a step contains no host synchronisation.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import Dict, Optional, Tuple
 
@@ -97,13 +98,20 @@ class ADMMBasedOptimizer(object):
                    full data, as `torchrun demo.py` would; each keeps its contiguous slice) or
                    'presharded' (each rank passes only its own samples).
       use_tensor_cores  None = automatic (tcgen05 path when the shape is eligible).
+      probe        how the backtracking loop of the weight updates (admm.py:331-338) gets f(w + G/theta): 'moments'
+                   (default; one pass, every theta at once from a 4th-order expansion along the probe ray, valid because
+                   the perturbation of the pre-activations is < 2^-5 there -- checked on the device, exact passes follow if
+                   not) or 'exact' (every candidate evaluated one by one).  Both replay the same comparison; they can
+                   stop at different thetas only where the reference's own fp32 comparison is decided by rounding
+                   (the "absorption exits" of SURVEY section 7), with no effect on the iterates at the parity tolerance.
     """
 
     def __init__(self, model, training_samples: Tuple[torch.Tensor, torch.Tensor],
                  parameter_dictionary: Optional[Dict[str, Dict[str, float]]] = None, verbose: bool = True, *,
                  variant: Optional[str] = None, with_dual_y: bool = False, sharding: str = "slice",
                  use_tensor_cores: Optional[bool] = None, scratch_bytes: Optional[int] = None,
-                 comm: Optional[Comm] = None, keep_preactivations: Optional[bool] = None) -> None:
+                 comm: Optional[Comm] = None, keep_preactivations: Optional[bool] = None,
+                 probe: Optional[str] = None) -> None:
         self._lib = _lib.load()
         self.device = _require_cuda()
         if self._lib.admm_device_ok() <= 0:
@@ -112,6 +120,8 @@ class ADMMBasedOptimizer(object):
         log_assert(variant in _VARIANTS, f"variant must be one of {list(_VARIANTS)} (Got: {variant}).")
         log_assert(not (with_dual_y and variant == "no_dual_y"), "with_dual_y needs variant='admm'.")
         self.variant, self.with_dual_y = variant, bool(with_dual_y)
+        self.probe = probe or os.environ.get("ADMM_LSTM_PROBE", "moments")
+        log_assert(self.probe in ("moments", "exact"), f"probe must be 'moments' or 'exact' (Got: {self.probe}).")
         self.verbose = verbose
         self.summary = None
         self.comm = comm if comm is not None else Comm()
@@ -167,12 +177,15 @@ class ADMMBasedOptimizer(object):
         self._grad = torch.zeros(4 * kmax * H, dtype=f32, device=dev)
         self._done = torch.zeros(12, dtype=torch.int32, device=dev)      # [0,4) decided, [4,12) diagnostics
         self._theta_w = torch.zeros(8, dtype=f32, device=dev)       # [src][gate]
+        self._qmax = torch.zeros(4, dtype=f32, device=dev)          # max |Q| per gate of the current probe pass
+        self._qmax_w = torch.zeros(8, dtype=f32, device=dev)        # [src][gate]: the same, kept for the next plans
         self._theta_h = torch.zeros(1, dtype=f32, device=dev)
         # ring of pinned read-backs of the chosen thetas: the host runs ahead of the device (it is throttled only
         # by the launch queue), so the hint for step s usually comes from step s-2
-        self._theta_ring = [[torch.zeros(9, dtype=f32).pin_memory(), None, -1] for _ in range(4)]
+        self._theta_ring = [[torch.zeros(17, dtype=f32).pin_memory(), None, -1] for _ in range(4)]
         self._step_index = 0
         self._hint = None            # per src: exit exponents of step s-2 (list of 4) or None
+        self._hint_q = None          # per src: max |Q| per gate of step s-2 or None
 
         # scratch of the weight phase: R^T for the gradient pass, Z0 and Q for the probe pass -> 8*H*ldn floats
         # per timestep of a chunk
@@ -401,35 +414,47 @@ class ADMMBasedOptimizer(object):
         want = self._step_index - 2
         slot = self._theta_ring[want % len(self._theta_ring)] if want >= 0 else None
         if slot is None or slot[2] != want:
-            self._hint = None
+            self._hint = self._hint_q = None
             return
         slot[1].synchronize()
         th = slot[0][:8].view(2, 4)
         # theta_out = 2^(k-1) for exit index k (0.5 -> k = 0)
         self._hint = {src: [int(v).bit_length() if v >= 1.0 else 0 for v in th[src].tolist()]
                       for src in (_lib.SRC_X, _lib.SRC_H)}
+        self._hint_q = {src: slot[0][9 + 4 * src: 13 + 4 * src].tolist() for src in (_lib.SRC_X, _lib.SRC_H)}
 
     def _probe_plans(self, src: int):
-        """First pass: a window of candidates around the previous exit index of each gate, everything below the
-        window represented by lower-bound sums on 1/8 of the units (admm_probe_plan); then full passes from 0.
-        Window = [k* - 5, k* + 2]: the bound proves `f > est` only with a margin of 8x, which the quadratic growth of
-        f along the step gives ~4 doublings below the exit."""
-        full = [((0, 0, 0, 0), _lib.ADMM_MAX_CAND, 0), ((32, 32, 32, 32), _lib.ADMM_MAX_CAND, 0)]
-        if self._hint is None:
-            return full
-        ks = self._hint[src]
-        k0 = [max(0, min(k - 5, _lib.ADMM_MAX_CAND)) for k in ks]
-        span = max(k + 3 - a for k, a in zip(ks, k0))
-        ncand = min(_lib.ADMM_MAX_CAND, max(8, -(-span // 8) * 8))
-        first = (tuple(k0), ncand, int(any(k0)))
-        return [first] + full
+        """First pass: the moment pass (admm_probe_plan::moments) -- one activation per element gives f for every
+        candidate k >= k0 at once; k0 = first exponent at which the expansion is valid (max|Q| 2^-k0 <= 2^-6, from the
+        max|Q| of step s-2, one doubling of margin), everything below k0 represented by lower-bound sums.  On the
+        benchmark workloads k0 is 0..2.  Then, in case the expansion turns out not to be valid or a bound fails, exact
+        32-candidate passes from 0 (launched speculatively, they exit at once when all four gates are decided)."""
+        full = [((0, 0, 0, 0), _lib.ADMM_MAX_CAND, 0, 0), ((32, 32, 32, 32), _lib.ADMM_MAX_CAND, 0, 0)]
+        if self.probe == "exact":
+            # every candidate evaluated one by one: a window of 8 around the exit of step s-2, lower-bound proofs on
+            # 1/8 (5/8 next to the window) of the units below it.  Window = [k* - 5, k* + 2]: the bound proves `f > est`
+            # only with a margin of 8x, which the quadratic growth of f along the step gives ~4 doublings below the exit.
+            if self._hint is None:
+                return full
+            ks = self._hint[src]
+            k0 = [max(0, min(k - 5, _lib.ADMM_MAX_CAND)) for k in ks]
+            span = max(k + 3 - a for k, a in zip(ks, k0))
+            ncand = min(_lib.ADMM_MAX_CAND, max(8, -(-span // 8) * 8))
+            return [(tuple(k0), ncand, int(any(k0)), 0)] + full
+        k0 = [0, 0, 0, 0]
+        if self._hint_q is not None:
+            for g, q in enumerate(self._hint_q[src]):
+                if q == q and q > 2.0 ** -6:                      # NaN-safe
+                    k0[g] = min(_lib.ADMM_MAX_CAND, int(math.ceil(math.log2(q * 64.0))) + 1) if math.isfinite(q) else _lib.ADMM_MAX_CAND
+        return [(tuple(k0), 1, int(any(k0)), 1)] + full
 
     def _push_theta_hint(self) -> None:
         slot = self._theta_ring[self._step_index % len(self._theta_ring)]
         if slot[1] is not None:
             slot[1].synchronize()       # four steps old: long finished
         slot[0][:8].copy_(self._theta_w, non_blocking=True)
-        slot[0][8:].copy_(self._theta_h, non_blocking=True)
+        slot[0][8:9].copy_(self._theta_h, non_blocking=True)
+        slot[0][9:].copy_(self._qmax_w, non_blocking=True)
         slot[1] = torch.cuda.Event()
         slot[1].record()
         slot[2] = self._step_index
@@ -484,18 +509,23 @@ class ADMMBasedOptimizer(object):
         self._done.zero_()
         theta_ptr = self._theta_w[4 * src:].data_ptr()
         plans = self._probe_plans(src)
-        for q, (k0, ncand, proof) in enumerate(plans):
+        for q, (k0, ncand, proof, moments) in enumerate(plans):
             plan = _lib.ProbePlan()
             for g in range(4):
                 plan.k0[g] = k0[g]
-            plan.ncand, plan.proof = ncand, proof
+            plan.ncand, plan.proof, plan.moments = ncand, proof, moments
             self._acc_fk.zero_()
+            if moments:
+                self._qmax.zero_()
             for t0, tc in chunks:
                 self._call("admm_weight_probe", pp, src, t0, tc, self._scratch.data_ptr(), self._grad.data_ptr(),
-                           C.byref(plan), self._done.data_ptr(), self._acc_fk.data_ptr(), st)
+                           C.byref(plan), self._done.data_ptr(), self._acc_fk.data_ptr(), self._qmax.data_ptr(), st)
             self.comm.allreduce_sum_(self._acc_fk)
-            self._call("admm_weight_select", pp, src, self._acc_est.data_ptr(), self._acc_fk.data_ptr(), C.byref(plan),
-                       int(q == len(plans) - 1), self._done.data_ptr(), theta_ptr, st)
+            if moments:
+                self.comm.allreduce_max_(self._qmax)
+                self._qmax_w[4 * src: 4 * src + 4].copy_(self._qmax)
+            self._call("admm_weight_select", pp, src, self._acc_est.data_ptr(), self._acc_fk.data_ptr(), self._qmax.data_ptr(),
+                       C.byref(plan), int(q == len(plans) - 1), self._done.data_ptr(), theta_ptr, st)
         self._call("admm_weight_apply", pp, src, self._grad.data_ptr(), theta_ptr, st)
 
     def __update_last(self, st) -> None:
@@ -518,7 +548,7 @@ class ADMMBasedOptimizer(object):
             "n_global": self.n_global, "rank": self.comm.rank, "world_size": self.comm.world_size,
             "rho": {k: float(v) for k, v in self.rhos.items()}, "beta": {k: float(v) for k, v in self.betas.items()},
             "step_index": self._step_index,
-            "theta_w": self._theta_w.cpu(), "theta_h": self._theta_h.cpu(),
+            "theta_w": self._theta_w.cpu(), "theta_h": self._theta_h.cpu(), "qmax_w": self._qmax_w.cpu(),
             "gates": {k: self.gates[k].cpu().contiguous() for k in _STATE_KEYS + ("a",)},
             "duals": {k: self.duals[k].cpu().contiguous() for k in ("i", "f", "g", "o", "c", "y")},
             "dual_h_T": self._dual_h.t()[: self.n_local].cpu().contiguous(),
@@ -541,6 +571,7 @@ class ADMMBasedOptimizer(object):
         self._dual_y[:, :n] = sd["duals"]["y"].to(dev).t()
         self._theta_w.copy_(sd["theta_w"])
         self._theta_h.copy_(sd["theta_h"])
+        self._qmax_w.copy_(sd.get("qmax_w", torch.zeros(8)))
         # the probe-window hint of the next two steps comes from the saved thetas (the ring is empty after a restart)
         self._step_index = int(sd["step_index"])
         for slot in self._theta_ring:
@@ -550,7 +581,8 @@ class ADMMBasedOptimizer(object):
             if idx >= 0:
                 slot = self._theta_ring[idx % len(self._theta_ring)]
                 slot[0][:8].copy_(sd["theta_w"])
-                slot[0][8:].copy_(sd["theta_h"])
+                slot[0][8:9].copy_(sd["theta_h"])
+                slot[0][9:].copy_(sd.get("qmax_w", torch.zeros(8)))
                 slot[1] = torch.cuda.Event()
                 slot[1].record()
                 slot[2] = idx

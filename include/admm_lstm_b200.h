@@ -44,7 +44,8 @@ extern "C" {
 #define ADMM_MAX_O 16         /* output_size limit of the t = T kernels */
 #define ADMM_MAX_CAND 32      /* theta candidates per probe pass                                   */
 #define ADMM_EST_CAND 64      /* est() sums are precomputed for theta = 2^0 .. 2^63                 */
-#define ADMM_FK_SLOTS 65      /* [0,32) window candidates, [32] f(w), [33,65) lower-bound sums k<32 */
+#define ADMM_FK_SLOTS 72      /* [0,32) window candidates, [32] f(w), [33,65) lower-bound sums k<32, [65,70) moments */
+#define ADMM_FK_MOMENTS 65    /* F0 = f(w) sum, then B1..B4 of the expansion below                                    */
 #define ADMM_N_METRICS 8
 
 /* rho / beta in the reference's own key order (admm.py:131-160, parameters.py). */
@@ -61,11 +62,23 @@ typedef struct admm_hyper {
  * three exponents next to the window) -> fk_acc[g][33+k].  A
  * partial sum of squares is a rigorous LOWER bound of f(w + G/2^k); if even the bound exceeds est_k the
  * reference's loop provably continues past k (admm.py:334) without the full evaluation.  If a bound does
- * not prove it, the pass stays undecided for that gate and a full pass from k = 0 follows. */
+ * not prove it, the pass stays undecided for that gate and a full pass from k = 0 follows.
+ *
+ * moments != 0 (the normal first pass): no candidate is evaluated one by one.  With delta = Q 2^-k the perturbation of the
+ * pre-activation, act(z + delta) = act(z) + a1 delta + a2 delta^2 + a3 delta^3 + a4 delta^4 + O(delta^5), so
+ *      f(w + G/2^k) - f(w) = sum_j B_j 2^(-jk),   B_j = sum over elements of c_j(z, u) Q^j   (u = act z - lambda/rho - gate,
+ *      c_1 = 2 u a1, c_2 = 2 u a2 + a1^2, c_3 = 2 u a3 + 2 a1 a2, c_4 = 2 u a4 + 2 a1 a3 + a2^2)
+ * and ONE pass with ONE activation per element (-> fk_acc[g][65..69] = F0, B1..B4 and qmax[g] = max |Q|) gives f for every
+ * k >= k0[g] with max|Q| 2^-k0 <= 2^-5, where the truncated term is < 3e-9 of the leading one -- below the rounding of
+ * the reference's own fp32 evaluation (measured: max |delta| at the exit is 1e-4 .. 1e-7 on the benchmark workloads).
+ * Candidates k < k0[g] (perturbation too large for the expansion; usually none) are handled by the lower-bound proofs
+ * above; if the expansion is not valid at k0[g] the gate stays undecided and the exact passes follow. */
 typedef struct admm_probe_plan {
   int32_t k0[4];
   int32_t ncand;
   int32_t proof;
+  int32_t moments;
+  int32_t reserved_;
 } admm_probe_plan;
 
 /* One rank's shard of the problem.  The optimizer owns every buffer (allocated by the host
@@ -150,7 +163,8 @@ int admm_wy_apply(const admm_problem* p, const double* g_acc, void* stream);
  *           comparison come from the same kernel); writes theta_out[g] (already halved, admm.py:338) and
  *           done[g]; leaves the gate undecided if a lower bound failed or no candidate exits.  `done` has 12
  *           entries: [0,4) decided flags, [4,8) diagnostics of the last undecided pass (1 = bound not conclusive,
- *           2 = window exhausted), [8,12) the exponent concerned.
+ *           2 = window exhausted, 3 = expansion not valid at k0), [8,12) the exponent concerned.  qmax: 4 floats
+ *           (max |Q| per gate, zeroed before the pass, MAX-reduced over shards), used by moments plans only.
  *  apply  : w <- (0.5 rho T theta w - G)/(beta + 0.5 rho theta T)           (admm.py:340-343)
  * K = D for ADMM_SRC_X, H for ADMM_SRC_H. */
 /* begin: once per `src` before the first admm_weight_grad of the phase (prepares the zstore refresh operands).
@@ -162,8 +176,8 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
 int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc, float* grad_out,
                             double* est_acc, void* stream);
 int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scratch, const float* grad,
-                      const admm_probe_plan* plan, const int32_t* done, double* fk_acc, void* stream);
-int admm_weight_select(const admm_problem* p, int src, const double* est_acc, const double* fk_acc,
+                      const admm_probe_plan* plan, const int32_t* done, double* fk_acc, float* qmax, void* stream);
+int admm_weight_select(const admm_problem* p, int src, const double* est_acc, const double* fk_acc, const float* qmax,
                        const admm_probe_plan* plan, int final_pass, int32_t* done, float* theta_out,
                        void* stream);
 int admm_weight_apply(const admm_problem* p, int src, const float* grad, const float* theta,

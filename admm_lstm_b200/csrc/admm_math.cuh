@@ -62,6 +62,44 @@ struct FastMath {
   __device__ __forceinline__ static float div(float a, float b) { return a * rcp(b); }
 };
 #endif
+#if defined(__CUDACC__)
+// Coefficients of (act(z + d) - c)^2 - (act(z) - c)^2 = c1 d + c2 d^2 + ... + c6 d^6 + O(d^7) with s = act(z),
+// u = act(z) - c (the moment pass of the backtracking probes, include/admm_lstm_b200.h admm_probe_plan::moments).
+// a_j = act^(j)(z) / j!; for |d| <= 2^-4 the truncated terms are < 2e-10 (tanh) / 1e-12 (sigmoid) -- checked against
+// float64 in scripts/ and by test_moment_probe_equals_exact_probe.
+__device__ __forceinline__ void moment_terms(bool is_g, float s, float u, float (&c)[6]) {
+  float a1, a2, a3, a4, a5, a6;
+  if (is_g) {
+    // tanh (t = s, D1 = 1 - t^2): D2 = -2 t D1, D3 = -2 D1 (1 - 3 t^2), D4 = 8 t D1 (2 - 3 t^2),
+    // D5 = 8 D1 (2 - 15 t^2 + 15 t^4), D6 = -16 t D1 (17 - 60 t^2 + 45 t^4)
+    const float t2 = s * s, d1 = 1.0f - t2;
+    a1 = d1;
+    a2 = -s * d1;
+    a3 = (-1.0f / 3.0f) * d1 * fmaf(-3.0f, t2, 1.0f);
+    a4 = (1.0f / 3.0f) * s * d1 * fmaf(-3.0f, t2, 2.0f);
+    a5 = (1.0f / 15.0f) * d1 * fmaf(fmaf(15.0f, t2, -15.0f), t2, 2.0f);
+    a6 = (-1.0f / 45.0f) * s * d1 * fmaf(fmaf(45.0f, t2, -60.0f), t2, 17.0f);
+  } else {
+    // sigmoid (D1 = s (1 - s), m = 1 - 2 s): D2 = D1 m, D3 = D1 (1 - 6 D1), D4 = D1 m (1 - 12 D1),
+    // D5 = D1 (1 - 30 D1 + 120 D1^2), D6 = D1 m (1 - 60 D1 + 360 D1^2)
+    const float d1 = s * (1.0f - s), m = fmaf(-2.0f, s, 1.0f), dm = d1 * m;
+    a1 = d1;
+    a2 = 0.5f * dm;
+    a3 = (1.0f / 6.0f) * d1 * fmaf(-6.0f, d1, 1.0f);
+    a4 = (1.0f / 24.0f) * dm * fmaf(-12.0f, d1, 1.0f);
+    a5 = (1.0f / 120.0f) * d1 * fmaf(fmaf(120.0f, d1, -30.0f), d1, 1.0f);
+    a6 = (1.0f / 720.0f) * dm * fmaf(fmaf(360.0f, d1, -60.0f), d1, 1.0f);
+  }
+  const float u2 = 2.0f * u;
+  c[0] = u2 * a1;
+  c[1] = fmaf(u2, a2, a1 * a1);
+  c[2] = fmaf(u2, a3, 2.0f * a1 * a2);
+  c[3] = fmaf(u2, a4, fmaf(2.0f * a1, a3, a2 * a2));
+  c[4] = fmaf(u2, a5, 2.0f * fmaf(a1, a4, a2 * a3));
+  c[5] = fmaf(u2, a6, fmaf(2.0f, fmaf(a1, a5, a2 * a4), a3 * a3));
+}
+#endif
+
 // admm.py:239-244, expressed through the activation value itself
 ADMM_HD float dsigmoid_from(float s) { return s * (1.0f - s); }
 ADMM_HD float dtanh_from(float t) { return 1.0f - t * t; }

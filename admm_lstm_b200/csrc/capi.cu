@@ -237,11 +237,12 @@ int admm_weight_finish_grad(const admm_problem* p, int src, const double* g_acc,
 
 static int check_plan(const admm_probe_plan* plan, const char* who) {
   ADMM_REQUIRE(plan, "%s: null plan", who);
-  ADMM_REQUIRE(plan->moments || (plan->ncand >= 1 && plan->ncand <= ADMM_MAX_CAND), "%s: bad ncand %d", who, plan->ncand);
+  ADMM_REQUIRE(plan->ncand >= (plan->moments ? 0 : 1) && plan->ncand <= ADMM_MAX_CAND, "%s: bad ncand %d", who, plan->ncand);
   for (int g = 0; g < 4; ++g) {
     ADMM_REQUIRE(plan->k0[g] >= 0 && plan->k0[g] + (plan->moments ? 0 : plan->ncand) <= ADMM_EST_CAND, "%s: bad k0[%d]=%d", who,
                  g, plan->k0[g]);
-    ADMM_REQUIRE(!plan->proof || plan->k0[g] <= ADMM_MAX_CAND, "%s: proof range too long", who);
+    ADMM_REQUIRE(!plan->proof || plan->k0[g] + (plan->moments ? plan->ncand : 0) <= ADMM_MAX_CAND, "%s: proof range too long",
+                 who);
   }
   return ADMM_OK;
 }
@@ -276,6 +277,13 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
   e.jmod = 1; e.jrem = 0; e.publish_fw = 1;
   rc = plan->moments ? probe_moments(e, qmax, st) : probe_eval(e, st);
   if (rc || !plan->proof) return rc;
+  if (plan->moments) {
+    // insurance below the expansion: lower bounds of f for k < k0 + ncand on 1/8 of the units (these exponents are many
+    // doublings below the exit, so the bound exceeds est by orders of magnitude; see weight_select_kernel)
+    for (int g = 0; g < 4; ++g) { e.kbase[g] = 0; e.nc[g] = plan->k0[g] + plan->ncand; e.slot0[g] = ADMM_MAX_CAND + 1; }
+    e.jmod = 8; e.jrem = 0; e.publish_fw = 0;
+    return probe_eval(e, st);
+  }
   // lower bounds below the window: every k < k0[g] on unit blocks 0 mod 8, and the three exponents next to the
   // window additionally on the odd blocks (disjoint sets, so the sums add up to one partial sum over 5/8 of the units)
   for (int g = 0; g < 4; ++g) { e.kbase[g] = 0; e.nc[g] = plan->k0[g]; e.slot0[g] = ADMM_MAX_CAND + 1; }

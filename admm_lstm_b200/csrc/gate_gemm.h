@@ -8,7 +8,7 @@
 
 namespace admm {
 
-enum GateGemmMode { GG_FORWARD = 0, GG_SWEEP = 1, GG_GRAD = 2, GG_PROBE = 3, GG_RAWZ = 7 /* debug: Z -> scratch */ };
+enum GateGemmMode { GG_FORWARD = 0, GG_SWEEP = 1, GG_GRAD = 2, GG_PROBE = 3, GG_RAWZ = 7 /* Z -> scratch */ };
 
 // All pointers are pre-offset to the first timestep of the launch (grid.z index tl = 0);
 // x_tstride / s_tstride are the element strides from one timestep slab to the next.

@@ -152,39 +152,14 @@ __global__ void __launch_bounds__(NT) probe_eval_kernel(const ProbeEvalArgs p, i
 // ------------------------------------------------------------------------------------------------------------------
 // Moment pass (admm_probe_plan::moments).  Along the probe ray the perturbation of the pre-activation is delta = Q 2^-k;
 // at and above the exit of the backtracking loop it is tiny (measured 1e-4 .. 1e-7 on the benchmark workloads), so
-//     u_k = u + a1 d + a2 d^2 + a3 d^3 + a4 d^4 + O(d^5),   a_j = act^(j)(z) / j!,   u = act(z) - lambda/rho - gate
-//     u_k^2 - u^2 = c1 d + c2 d^2 + c3 d^3 + c4 d^4 + O(d^5)
+//     u_k = u + a1 d + ... + a6 d^6 + O(d^7),   a_j = act^(j)(z) / j!,   u = act(z) - lambda/rho - gate
+//     u_k^2 - u^2 = c1 d + c2 d^2 + ... + c6 d^6 + O(d^7)
 // and the sums B_j = sum c_j Q^j give f for EVERY candidate at once -- one activation per element instead of one per
-// element and candidate.  Q is normalised by 2^-k0 (t = Q 2^-k0, |t| <= 2^-5 where the expansion is used) so that the
+// element and candidate.  Q is normalised by 2^-k0 (t = Q 2^-k0, |t| <= 2^-4 where the expansion is used) so that the
 // fp32 partial sums stay in range; the block totals are rescaled by 2^(j k0) in fp64.
-__device__ __forceinline__ void moment_terms(bool is_g, float s, float u, float (&c)[4]) {
-  float a1, a2, a3, a4;
-  if (is_g) {
-    // tanh (t = s): D1 = 1 - t^2, D2 = -2 t D1, D3 = -2 D1 (D1 - 2 t^2), D4 = 8 t D1 (2 D1 - t^2); a_j = D_j / j!
-    const float d1 = 1.0f - s * s;
-    a1 = d1;
-    a2 = -s * d1;
-    a3 = (-1.0f / 3.0f) * d1 * (d1 - 2.0f * s * s);
-    a4 = (1.0f / 3.0f) * s * d1 * (2.0f * d1 - s * s);
-  } else {
-    // sigmoid: D1 = s (1 - s), D2 = D1 (1 - 2 s), D3 = D1 (1 - 6 D1), D4 = D2 (1 - 12 D1); a_j = D_j / j!
-    const float d1 = s * (1.0f - s);
-    const float d2 = d1 * (1.0f - 2.0f * s);
-    a1 = d1;
-    a2 = 0.5f * d2;
-    a3 = (1.0f / 6.0f) * d1 * (1.0f - 6.0f * d1);
-    a4 = (1.0f / 24.0f) * d2 * (1.0f - 12.0f * d1);
-  }
-  const float u2 = 2.0f * u;
-  c[0] = u2 * a1;
-  c[1] = fmaf(u2, a2, a1 * a1);
-  c[2] = fmaf(u2, a3, 2.0f * a1 * a2);
-  c[3] = fmaf(u2, a4, fmaf(2.0f * a1, a3, a2 * a2));
-}
-
 __global__ void __launch_bounds__(NT) probe_moments_kernel(const ProbeEvalArgs p, float* qmax, int n_jb, int n_nb,
                                                            int64_t n_items) {
-  __shared__ float red[6 * (NT / 32)];
+  __shared__ float red[8 * (NT / 32)];
   if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -197,7 +172,7 @@ __global__ void __launch_bounds__(NT) probe_moments_kernel(const ProbeEvalArgs p
     const float sn = __int_as_float((127 - kn) << 23);                  // 2^-k0
     const int64_t n = ((int64_t)nb * NT + threadIdx.x) * 4;
     const int j0 = jb * JB;
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float tmax = 0.f;
     const float rho = p.rho[g];
     const float inv_rho = 1.0f / rho;
@@ -221,35 +196,37 @@ __global__ void __launch_bounds__(NT) probe_moments_kernel(const ProbeEvalArgs p
           const float lr = rho_pow2 ? lam[e] * inv_rho : __fdiv_rn(lam[e], rho);
           const float s = (g == 2) ? FastMath::tanh(z[e]) : FastMath::sigmoid(z[e]);
           const float u = (s - lr) - gv[e];
-          float c[4];
+          float c[6];
           moment_terms(g == 2, s, u, c);
-          const float t = q[e] * sn, t2 = t * t;
+          const float t = q[e] * sn, t2 = t * t, t3 = t2 * t;
           acc[0] = fmaf(u, u, acc[0]);
           acc[1] = fmaf(c[0], t, acc[1]);
           acc[2] = fmaf(c[1], t2, acc[2]);
-          acc[3] = fmaf(c[2] * t, t2, acc[3]);
+          acc[3] = fmaf(c[2], t3, acc[3]);
           acc[4] = fmaf(c[3] * t2, t2, acc[4]);
+          acc[5] = fmaf(c[4] * t2, t3, acc[5]);
+          acc[6] = fmaf(c[5] * t3, t3, acc[6]);
           tmax = fmaxf(tmax, fabsf(q[e]));
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < 7; ++k) {
       const float sm = warp_sum(acc[k]);
       if (lane == 0) red[k * (NT / 32) + warp] = sm;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    if (lane == 0) red[5 * (NT / 32) + warp] = tmax;
+    if (lane == 0) red[7 * (NT / 32) + warp] = tmax;
     __syncthreads();
-    if (threadIdx.x < 5) {
+    if (threadIdx.x < 7) {
       const int k = threadIdx.x;
       double sm = 0.0;
       for (int w = 0; w < NT / 32; ++w) sm += (double)red[k * (NT / 32) + w];
       atomicAdd(p.fk_acc + g * NCS + ADMM_FK_MOMENTS + k, ldexp(sm, k * kn));      // B_k in units of Q^k, not t^k
-    } else if (threadIdx.x == 5) {
+    } else if (threadIdx.x == 7) {
       float m = 0.f;
-      for (int w = 0; w < NT / 32; ++w) m = fmaxf(m, red[5 * (NT / 32) + w]);
+      for (int w = 0; w < NT / 32; ++w) m = fmaxf(m, red[7 * (NT / 32) + w]);
       atomicMax(reinterpret_cast<unsigned int*>(qmax + g), __float_as_uint(m));
     }
     __syncthreads();

@@ -335,25 +335,27 @@ __global__ void weight_select_kernel(const double* est_acc, const double* fk_acc
     return f_w + (float)es[2 * k] + ((float)T * 0.5f * theta) * (float)es[2 * k + 1];
   };
   const int k0 = plan.k0[g];
-  if (plan.proof) {
-    for (int k = 0; k < k0; ++k) {
+  if (plan.moments) {
+    // f(w + G/2^k) = F0 + B1 x + ... + B6 x^6, x = 2^-k, valid where max|Q| x <= 2^-4 (admm_probe_plan).  kv = first
+    // exponent at which it is; every k < kv must be covered by a lower bound that proves the loop continues past it.
+    int kv = k0;
+    while (kv < ADMM_EST_CAND && !(ldexpf(qmax[g], -kv) <= 0.0625f)) ++kv;
+    const int kp = plan.proof ? k0 + plan.ncand : 0;
+    if (kv > kp && kv > 0) {
+      done[4 + g] = 3; done[8 + g] = kv;             // expansion not valid where the bounds end: exact passes follow
+      return;
+    }
+    for (int k = 0; k < kv; ++k) {
       const float lower = 0.5f * rho * (float)fk[ADMM_MAX_CAND + 1 + k];
-      if (!(lower > est(k))) {                       // not provable from the subsample: a full pass will decide
+      if (!(lower > est(k))) {
         done[4 + g] = 1; done[8 + g] = k;
         return;
       }
     }
-  }
-  if (plan.moments) {
-    // f(w + G/2^k) = F0 + B1 x + B2 x^2 + B3 x^3 + B4 x^4, x = 2^-k, valid where max|Q| x <= 2^-5 (admm_probe_plan)
-    if (!(ldexpf(qmax[g], -k0) <= 0.03125f)) {
-      done[4 + g] = 3; done[8 + g] = k0;
-      return;
-    }
     const double* m = fk + ADMM_FK_MOMENTS;
-    for (int k = k0; k < ADMM_EST_CAND; ++k) {
+    for (int k = kv; k < ADMM_EST_CAND; ++k) {
       const double x = ldexp(1.0, -k);
-      const double f_k = m[0] + x * (m[1] + x * (m[2] + x * (m[3] + x * m[4])));
+      const double f_k = m[0] + x * (m[1] + x * (m[2] + x * (m[3] + x * (m[4] + x * (m[5] + x * m[6])))));
       const float f_b = 0.5f * rho * (float)f_k;
       if (!(f_b > est(k))) {
         theta_out[g] = ldexpf(1.0f, k - 1);          // theta /= 2 (admm.py:338)
@@ -364,6 +366,15 @@ __global__ void weight_select_kernel(const double* est_acc, const double* fk_acc
     theta_out[g] = ldexpf(1.0f, ADMM_EST_CAND - 1);   // iteration cap (the reference has none)
     done[g] = 1;
     return;
+  }
+  if (plan.proof) {
+    for (int k = 0; k < k0; ++k) {
+      const float lower = 0.5f * rho * (float)fk[ADMM_MAX_CAND + 1 + k];
+      if (!(lower > est(k))) {                       // not provable from the subsample: a full pass will decide
+        done[4 + g] = 1; done[8 + g] = k;
+        return;
+      }
+    }
   }
   int found = -1;
   for (int c = 0; c < plan.ncand; ++c) {

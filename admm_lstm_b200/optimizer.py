@@ -425,8 +425,8 @@ class ADMMBasedOptimizer(object):
 
     def _probe_plans(self, src: int):
         """First pass: the moment pass (admm_probe_plan::moments) -- one activation per element gives f for every
-        candidate k >= k0 at once; k0 = first exponent at which the expansion is valid (max|Q| 2^-k0 <= 2^-6, from the
-        max|Q| of step s-2, one doubling of margin), everything below k0 represented by lower-bound sums.  On the
+        candidate k >= k0 at once; k0 = first exponent at which the expansion is valid with a factor 2 to spare
+        (max|Q| 2^-k0 <= 2^-5 against the limit 2^-4, from the max|Q| of step s-2), everything below k0 represented by lower-bound sums.  On the
         benchmark workloads k0 is 0..2.  Then, in case the expansion turns out not to be valid or a bound fails, exact
         32-candidate passes from 0 (launched speculatively, they exit at once when all four gates are decided)."""
         full = [((0, 0, 0, 0), _lib.ADMM_MAX_CAND, 0, 0), ((32, 32, 32, 32), _lib.ADMM_MAX_CAND, 0, 0)]
@@ -444,9 +444,11 @@ class ADMMBasedOptimizer(object):
         k0 = [0, 0, 0, 0]
         if self._hint_q is not None:
             for g, q in enumerate(self._hint_q[src]):
-                if q == q and q > 2.0 ** -6:                      # NaN-safe
-                    k0[g] = min(_lib.ADMM_MAX_CAND, int(math.ceil(math.log2(q * 64.0))) + 1) if math.isfinite(q) else _lib.ADMM_MAX_CAND
-        return [(tuple(k0), 1, int(any(k0)), 1)] + full
+                if q == q and q > 2.0 ** -5:                      # NaN-safe
+                    k0[g] = min(_lib.ADMM_MAX_CAND, int(math.ceil(math.log2(q * 32.0)))) if math.isfinite(q) else _lib.ADMM_MAX_CAND
+        # proofs always cover two exponents more than the hint asks for (ncand = 2): max|Q| may grow by 8x between the
+        # hint and this step before the exact passes are needed
+        return [(tuple(k0), 2, 1, 1)] + full
 
     def _push_theta_hint(self) -> None:
         slot = self._theta_ring[self._step_index % len(self._theta_ring)]

@@ -44,8 +44,8 @@ extern "C" {
 #define ADMM_MAX_O 16         /* output_size limit of the t = T kernels */
 #define ADMM_MAX_CAND 32      /* theta candidates per probe pass                                   */
 #define ADMM_EST_CAND 64      /* est() sums are precomputed for theta = 2^0 .. 2^63                 */
-#define ADMM_FK_SLOTS 72      /* [0,32) window candidates, [32] f(w), [33,65) lower-bound sums k<32, [65,70) moments */
-#define ADMM_FK_MOMENTS 65    /* F0 = f(w) sum, then B1..B4 of the expansion below                                    */
+#define ADMM_FK_SLOTS 72      /* [0,32) window candidates, [32] f(w), [33,65) lower-bound sums k<32, [65,72) moments */
+#define ADMM_FK_MOMENTS 65    /* F0 = f(w) sum, then B1..B6 of the expansion below                                    */
 #define ADMM_N_METRICS 8
 
 /* rho / beta in the reference's own key order (admm.py:131-160, parameters.py). */
@@ -65,12 +65,12 @@ typedef struct admm_hyper {
  * not prove it, the pass stays undecided for that gate and a full pass from k = 0 follows.
  *
  * moments != 0 (the normal first pass): no candidate is evaluated one by one.  With delta = Q 2^-k the perturbation of the
- * pre-activation, act(z + delta) = act(z) + a1 delta + a2 delta^2 + a3 delta^3 + a4 delta^4 + O(delta^5), so
+ * pre-activation, act(z + delta) = act(z) + a1 delta + ... + a6 delta^6 + O(delta^7), so
  *      f(w + G/2^k) - f(w) = sum_j B_j 2^(-jk),   B_j = sum over elements of c_j(z, u) Q^j   (u = act z - lambda/rho - gate,
- *      c_1 = 2 u a1, c_2 = 2 u a2 + a1^2, c_3 = 2 u a3 + 2 a1 a2, c_4 = 2 u a4 + 2 a1 a3 + a2^2)
- * and ONE pass with ONE activation per element (-> fk_acc[g][65..69] = F0, B1..B4 and qmax[g] = max |Q|) gives f for every
- * k >= k0[g] with max|Q| 2^-k0 <= 2^-5, where the truncated term is < 3e-9 of the leading one -- below the rounding of
- * the reference's own fp32 evaluation (measured: max |delta| at the exit is 1e-4 .. 1e-7 on the benchmark workloads).
+ *      c_1 = 2 u a1, c_2 = 2 u a2 + a1^2, c_3 = 2 u a3 + 2 a1 a2, ..., c_6 = 2 u a6 + 2 a1 a5 + 2 a2 a4 + a3^2)
+ * and ONE pass with ONE activation per element (-> fk_acc[g][65..71] = F0, B1..B6 and qmax[g] = max |Q|) gives f for every
+ * k >= k0[g] with max|Q| 2^-k0 <= 2^-4, where the truncated terms are < 2e-10 per element -- below the rounding of the
+ * reference's own fp32 evaluation (measured: max |delta| at the exit is 1e-4 .. 1e-7 on the benchmark workloads).
  * Candidates k < k0[g] (perturbation too large for the expansion; usually none) are handled by the lower-bound proofs
  * above; if the expansion is not valid at k0[g] the gate stays undecided and the exact passes follow. */
 typedef struct admm_probe_plan {

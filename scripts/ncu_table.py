@@ -16,7 +16,7 @@ def main(path):
             return f"{float(v):.3g}"
         except ValueError:
             return "-"
-    print("id | kernel | time | grid | regs | dram read | dram write | dram% | L2% | xu% | fma% | issue% | tf32 pipe% | top stalls")
+    print("id | kernel | time | grid | regs | dram read | dram write | dram% | L2% | xu% | fma% | issue% | tensor pipe active% | tensor operand (smem) pipe% | top stalls")
     for r in rows[2:]:
         name = g(r, "Kernel Name").replace("void unnamed>::", "").replace("unnamed>::", "")[:46]
         stalls = [(float(r[i] or 0), h) for i, h in enumerate(hdr)
@@ -32,7 +32,8 @@ def main(path):
                           f(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
                           f(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                           f(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                          f(r, "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"),
+                          f(r, "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
+                          f(r, "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                           st]))
 
 

@@ -1,6 +1,5 @@
-"""One small cfg3-shaped problem (T=16 -> a single time chunk) stepped 4 times: the target of the ncu captures.
-Kernel launches of {probe_eval, gate_gemm_tc, atr_tc}: 16 forward + 28 + 28 (steps without a theta hint) + 36 per
-steady-state step, so `-s 108 -c 22` captures the weight phase of step 3 and its first two sweep launches."""
+"""One small cfg3-shaped problem (T=16 -> a single time chunk): steady-state step bracketed by cudaProfilerStart/Stop,
+the target of `ncu --profile-from-start off --set full` (profiles/r01_ncu_full_*.txt)."""
 import sys, torch
 sys.path.insert(0, '.')
 from bench import make_data, bench_params
@@ -13,7 +12,12 @@ model = LSTM(D, H, O)
 with torch.no_grad():
     for k, v in w.items(): getattr(model, k).copy_(torch.from_numpy(v))
 opt = ADMMBasedOptimizer(model, (torch.from_numpy(x), torch.from_numpy(y)), bench_params("GoogleStock", N, H), verbose=False)
-for s in range(4):
+for s in range(6):
+    if s == 5:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     opt.step()
     torch.cuda.synchronize()
+    if s == 5:
+        torch.cuda.profiler.stop()
     print(s, opt.theta_trace())

@@ -525,3 +525,48 @@ def test_moment_probe_equals_exact_probe(shape, tc):
     for k in ("i", "f", "g", "o", "c", "h"):
         assert rel_err(a.gates[k].cpu().numpy(), b.gates[k].cpu().numpy()) < 1e-5, k
     print(f"moment vs exact probes: {same}/{total} identical thetas")
+
+
+@pytest.mark.parametrize("shape,tc", [((600, 4, 16, 64, 1), True), ((333, 3, 5, 12, 2), False)])
+def test_large_probe_steps_take_the_exact_passes(shape, tc):
+    """A state far from consistency (random gates and duals) makes the gradient, hence Q = A G, large: at the first
+    exponents the perturbation of the pre-activations is far outside the validity of the moment expansion.  The device
+    must notice (diagnostic code 3 / failed bounds), fall back to the exact candidate-by-candidate passes and still
+    reproduce the oracle's thetas and weights."""
+    _need_gpu()
+    from oracle.admm_oracle import OracleADMM
+    from gpu_utils import make_opt, load_state, weights_of
+    from admm_lstm_b200 import _lib
+    n, t, d, h, o = shape
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=17)
+    rng = np.random.default_rng(5)
+    st = {"gates": {}, "duals": {}}
+    for k in ("i", "f", "g", "o", "c", "h"):
+        st["gates"][k] = rng.uniform(-1, 1, (n, t + 1, h)).astype(np.float32)
+        st["gates"][k][:, 0] = 0
+        st["duals"][k] = (0.5 * rng.standard_normal((n, t + 1, h))).astype(np.float32)
+        st["duals"][k][:, 0] = 0
+    st["duals"]["h"][:, :t] = 0
+    st["gates"]["a"] = rng.random((n, o)).astype(np.float32)
+    st["duals"]["y"] = np.zeros((n, o), np.float32)
+    _, opt = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=tc)
+    load_state(opt, st)
+    ora = OracleADMM(w, x, y, GOOGLE, variant="admm", state=st)
+    s = torch.cuda.current_stream().cuda_stream
+    fell_back = False
+    for src, name in ((_lib.SRC_X, "x"), (_lib.SRC_H, "h")):
+        opt._ADMMBasedOptimizer__update_weights(src, s)
+        fell_back |= any(v != 0 for v in opt._done.cpu().tolist()[4:8])
+        for g in "ifgo":
+            ora.update_weights(name, g)
+    assert fell_back, "the test state was meant to push the moment pass out of its validity range"
+    th = opt.theta_trace()
+    for k, v in ora.trace.items():
+        if k in th:
+            assert abs(th[k] - v) <= 1e-6 * v, (k, th[k], v)
+    # with this state the new weights are ~ -G, a sum of N*T*H terms of both signs: the fp32 CUDA-core path is itself
+    # 5e-5 from the oracle here (summation order), the split-precision tensor-core path 1.4e-4
+    wg = weights_of(opt)
+    for k in WKEYS:
+        if k != "out":
+            assert rel_err(wg[k], ora.w[k]) < 5e-4, (k, rel_err(wg[k], ora.w[k]))

@@ -15,12 +15,11 @@
 // TMA (128B swizzle, boxes of 64 halfs x BK rows) lands them in the canonical MN-major layout, so there is no
 // transposed copy of the state or of the weights anywhere.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (one thread per sample row and half of the tile's units; TMEM lane == sample,
-// TMEM column == (gate, unit)); two warps share each TMEM lane quarter and split the columns.
-// The accumulator never leaves the SM: the epilogue reads it with tcgen05.ld and applies the same
-// closed forms as the CUDA-core path (admm_math.cuh); all its global accesses are 128-byte warp rows.
-// Two CTAs are resident per SM (2 x 256 TMEM columns), so one tile's epilogue overlaps the other's MMAs.
+// Persistent kernel, one CTA per SM (576 threads): warp 0 = TMA producer (4-stage ring), warp 1 = TMEM allocator + MMA
+// issuer (one lane), warps 2..17 = epilogue (thread = one sample row x 16 units; TMEM lane == sample, TMEM column ==
+// (gate, unit)).  The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the
+// MMAs of tile i+1; it never leaves the SM: the epilogue reads it with tcgen05.ld and applies the same closed forms as
+// the CUDA-core path (admm_math.cuh); all its global accesses are 128-byte warp rows.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>

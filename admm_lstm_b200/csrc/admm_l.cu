@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(NT) l_forward_kernel(const LSlot p) {
   const int64_t total = (int64_t)p.H * p.ldn;
   float bmax = 0.f;
   float gmax[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    const int64_t n = idx % p.ldn;
-    if (n >= p.n) continue;
+  for (int j = blockIdx.y; j < p.H; j += gridDim.y)
+  for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
+    const int64_t idx = (int64_t)j * p.ldn + n;
     float zz[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -138,34 +138,44 @@ __device__ __forceinline__ int l_cap_exp(unsigned max_bits) {
   frexpf(m, &e);
   return 13 - e;
 }
+// grid.x walks the samples two at a time (float2), grid.y the (timestep, unit) rows: no per-element division
 __global__ void __launch_bounds__(NT) l_pack_kernel(const LPack p) {
   const int64_t per_t = (int64_t)p.H * p.ldn;
-  const int64_t total = per_t * p.tc;
   const float r_scale = p.r16_hi ? ldexpf(1.0f, l_cap_exp(*p.r_bound)) : 1.0f;
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    const int tl = (int)(idx / per_t);
-    const int64_t rem = idx % per_t;
-    const int j = (int)(rem / p.ldn);
-    const int64_t n = rem % p.ldn;
-    const bool ok = n < p.n;
-    const int64_t so = (int64_t)(p.t0 + tl + 1) * per_t + rem;         // slot of timestep t
-    const int64_t sp = (int64_t)(p.t0 + tl) * per_t + rem;             // slot of h_{t-1}
-    // all loads first: the buffers are not declared restrict, so a store in between would serialise the round trips
-    float v[5];
+  const int rows = p.H * p.tc;
+  for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+    const int tl = row / p.H, j = row - tl * p.H;
+    for (int64_t n = ((int64_t)blockIdx.x * NT + threadIdx.x) * 2; n < p.ldn; n += (int64_t)gridDim.x * NT * 2) {
+      const int64_t rem = (int64_t)j * p.ldn + n;
+      const int64_t so = (int64_t)(p.t0 + tl + 1) * per_t + rem;         // slot of timestep t
+      const int64_t sp = (int64_t)(p.t0 + tl) * per_t + rem;             // slot of h_{t-1}
+      // all loads first: the buffers are not declared restrict, so a store in between would serialise the round trips
+      float2 v[5];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) v[g] = ok ? p.z[g][so] + p.lam_s[g][so] / p.rho_s : 0.f;
-    v[4] = ok ? p.h[sp] : 0.f;
+      for (int g = 0; g < 4; ++g) {
+        const float2 z = *reinterpret_cast<const float2*>(p.z[g] + so);
+        const float2 l = *reinterpret_cast<const float2*>(p.lam_s[g] + so);
+        v[g].x = z.x + l.x / p.rho_s;
+        v[g].y = z.y + l.y / p.rho_s;
+      }
+      v[4] = *reinterpret_cast<const float2*>(p.h + sp);
+      const bool ok0 = n < p.n, ok1 = n + 1 < p.n;
 #pragma unroll
-    for (int g = 0; g < 5; ++g) {
-      const int64_t ro = (((int64_t)g * p.H + j) * p.tc + tl) * p.ldn + n;
-      if (p.r16_hi) {
-        const float c = fminf(fmaxf(v[g] * r_scale, -65504.0f), 65504.0f);
-        const __half hh = __float2half_rn(c);
-        p.r16_hi[ro] = hh;
-        p.r16_lo[ro] = __float2half_rn(c - __half2float(hh));
-      } else {
-        p.r[ro] = v[g];
-        p.r_lo[ro] = tf32_lo(v[g]);
+      for (int g = 0; g < 5; ++g) {
+        if (!ok0) v[g].x = 0.f;
+        if (!ok1) v[g].y = 0.f;
+        const int64_t ro = (((int64_t)g * p.H + j) * p.tc + tl) * p.ldn + n;
+        if (p.r16_hi) {
+          const float c0 = fminf(fmaxf(v[g].x * r_scale, -65504.0f), 65504.0f);
+          const float c1 = fminf(fmaxf(v[g].y * r_scale, -65504.0f), 65504.0f);
+          const __half h0 = __float2half_rn(c0), h1 = __float2half_rn(c1);
+          *reinterpret_cast<__half2*>(p.r16_hi + ro) = __halves2half2(h0, h1);
+          *reinterpret_cast<__half2*>(p.r16_lo + ro) =
+              __halves2half2(__float2half_rn(c0 - __half2float(h0)), __float2half_rn(c1 - __half2float(h1)));
+        } else {
+          *reinterpret_cast<float2*>(p.r + ro) = v[g];
+          *reinterpret_cast<float2*>(p.r_lo + ro) = make_float2(tf32_lo(v[g].x), tf32_lo(v[g].y));
+        }
       }
     }
   }
@@ -209,8 +219,9 @@ __global__ void __launch_bounds__(NT) l_gates_kernel(const LSlot p, float* red_m
   const float ap_i = appro_sig(red_max[0]), ap_f = appro_sig(red_max[1]), ap_g = appro_tanh(red_max[2]),
               ap_o = appro_sig(red_max[3]);
   float mx = 0.f, so2 = 0.f;
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    if (idx % p.ldn >= p.n) continue;
+  for (int j = blockIdx.y; j < p.H; j += gridDim.y)
+  for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
+    const int64_t idx = (int64_t)j * p.ldn + n;
     const float Pi = p.P[idx], Pf = p.P[total + idx], Pg = p.P[2 * total + idx], Po = p.P[3 * total + idx];
     float i = p.gate[0][idx], f = p.gate[1][idx], g = p.gate[2][idx], o = p.gate[3][idx];
     const float ct = p.gate[4][idx], h = p.gate[5][idx], c_ = p.c_prev[idx];
@@ -293,8 +304,9 @@ __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* 
   const float appro_h = appro_tanh(red_max[4]);
   const float qua_o = (float)red_sum[0];
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    if (idx % p.ldn >= p.n) continue;
+  for (int j = blockIdx.y; j < p.H; j += gridDim.y)
+  for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
+    const int64_t idx = (int64_t)j * p.ldn + n;
     const LDualIn d = l_duals_load(p, idx, total);
     const float i = d.i, f = d.f, g = d.g, o = d.o, l9 = d.l9, l10 = d.l10;
     const float ct = p.gate[4][idx], h = p.gate[5][idx], c_ = p.c_prev[idx];
@@ -333,12 +345,10 @@ __global__ void __launch_bounds__(NT) l_form10_kernel(const float* h, const floa
 }
 // h_T = (Form1 - rho11 Form11 + theta h)/(rho10 + theta)   (:258)
 __global__ void __launch_bounds__(NT) l_last_h_kernel(const LSlot p, const float* wy, const float* tmp, const float* theta_h) {
-  const int64_t total = (int64_t)p.H * p.ldn;
   const float th = theta_h[0], r10 = p.hp.rho10, r11 = p.hp.rho11;
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    const int64_t n = idx % p.ldn;
-    if (n >= p.n) continue;
-    const int j = (int)(idx / p.ldn);
+  for (int j = blockIdx.y; j < p.H; j += gridDim.y)
+  for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
+    const int64_t idx = (int64_t)j * p.ldn + n;
     const float form1 = r10 * (tanhf(p.gate[4][idx]) * p.gate[3][idx] + p.lam10[idx] / r10);
     const float form11 = tmp[n] * wy[j];
     const float hn = (form1 - r11 * form11 + th * p.gate[5][idx]) / (r10 + th);
@@ -361,8 +371,9 @@ __global__ void __launch_bounds__(NT) l_last_a_kernel(const float* h, const floa
 __global__ void __launch_bounds__(NT) l_duals_kernel(const LSlot p) {
   const int64_t total = (int64_t)p.H * p.ldn;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    if (idx % p.ldn >= p.n) continue;
+  for (int j = blockIdx.y; j < p.H; j += gridDim.y)
+  for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
+    const int64_t idx = (int64_t)j * p.ldn + n;
     const LDualIn d = l_duals_load(p, idx, total);
     l_duals_store(p, idx, d, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx], acc);
   }
@@ -372,9 +383,22 @@ __global__ void __launch_bounds__(NT) l_duals_kernel(const LSlot p) {
 }
 
 // ---------------------------------------------------------------------------------------------------- host helpers
-unsigned ew_grid(int64_t total) {
-  const int64_t b = (total + NT - 1) / NT;
-  return (unsigned)(b < 148 * 8 ? b : 148 * 8);
+// 2-D grid of ~148*8 CTAs: x over the samples (two per thread), y over rows
+dim3 ew_grid2(int64_t ldn, int rows) {
+  const int64_t gx = (ldn / 2 + NT - 1) / NT;
+  int64_t gy = (148 * 8 + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  return dim3((unsigned)gx, (unsigned)gy);
+}
+
+// the same with one sample per thread
+dim3 ew_grid1(int64_t ldn, int rows) {
+  const int64_t gx = (ldn + NT - 1) / NT;
+  int64_t gy = (148 * 8 + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  return dim3((unsigned)gx, (unsigned)gy);
 }
 
 int validate_l(const admm_l_problem* lp, const char* who) {
@@ -445,7 +469,7 @@ int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, float* nex
   if (s == 1 && (rc = reset_bound(lp, st))) return rc;
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch, next_max);
-  l_forward_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k);
+  l_forward_kernel<<<ew_grid1(k.ldn, k.H), NT, 0, st>>>(k);
   count_launch();
   return check_launch("l_forward");
 }
@@ -478,7 +502,7 @@ int admm_l_sums(const admm_l_problem* lp, int t0, int tc, float* scratch, double
     k.r16_lo = reinterpret_cast<__half*>(scratch + half);
     k.r_bound = tc_r_bound(&b);
   }
-  l_pack_kernel<<<ew_grid((int64_t)b.H * b.ldn * tc), NT, 0, st>>>(k);
+  l_pack_kernel<<<ew_grid2(b.ldn, b.H * tc), NT, 0, st>>>(k);
   count_launch();
   if ((rc = check_launch("l_pack"))) return rc;
   AtrArgs r;
@@ -540,7 +564,7 @@ int admm_l_sweep_gates(const admm_l_problem* lp, int s, float* scratch, float* r
   if (s == 1 && (rc = reset_bound(lp, st))) return rc;       // the sweep re-measures the bound of the next packing pass
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch);
-  l_gates_kernel<<<ew_grid((int64_t)k.H * k.ldn), NT, 0, st>>>(k, red_max, red_sum);
+  l_gates_kernel<<<ew_grid1(k.ldn, k.H), NT, 0, st>>>(k, red_max, red_sum);
   count_launch();
   return check_launch("l_gates");
 }
@@ -551,7 +575,7 @@ int admm_l_sweep_cell(const admm_l_problem* lp, int s, const float* scratch, con
   if (rc) return rc;
   ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum && next_max, "admm_l_sweep_cell: bad arguments");
   const LSlot k = make_slot(lp, s, scratch, next_max);
-  const unsigned grid = ew_grid((int64_t)k.H * k.ldn);
+  const dim3 grid = ew_grid1(k.ldn, k.H);
   if (s == lp->base.T) l_cell_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
   else l_cell_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
   count_launch();
@@ -567,7 +591,7 @@ int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, cons
   cudaStream_t st = (cudaStream_t)stream;
   const LSlot k = make_slot(lp, b.T, scratch, next_max);
   const unsigned nb = (unsigned)((b.n + NT - 1) / NT);
-  const unsigned grid = ew_grid((int64_t)k.H * k.ldn);
+  const dim3 grid = ew_grid1(k.ldn, k.H);
   l_form10_kernel<<<nb, NT, 0, st>>>(k.gate[5], b.wy, b.a, b.dual_y, lp->hp.rho11, b.n, b.ldn, b.H, tmp);
   l_last_h_kernel<<<grid, NT, 0, st>>>(k, b.wy, tmp, theta_h);
   const float a_den = (float)(2.0 / (double)lp->hp.n_norm + (double)lp->hp.rho11);

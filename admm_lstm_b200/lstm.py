@@ -35,24 +35,43 @@ class LSTM(nn.Module):
         for param in self.parameters():
             nn.init.xavier_normal_(param)
 
-    # -- accessors used by the optimizer (reference blocks/lstm.py:31-41) --------------------------
+    # -- weight accessors the optimizer's drop-in surface exposes (reference blocks/lstm.py:31-41) ----
+    def _param(self, name: str) -> nn.Parameter:
+        return self._parameters[name]
+
     def get_weight(self, map_from: str, map_to: str) -> torch.Tensor:
-        return getattr(self, f"{map_from}2{map_to}").detach().clone()
+        return self._param(map_from + "2" + map_to).data.clone()
 
     def set_weight(self, map_from: str, map_to: str, value: torch.Tensor) -> None:
-        setattr(self, f"{map_from}2{map_to}", nn.Parameter(value.detach().clone()))
+        self._parameters[map_from + "2" + map_to] = nn.Parameter(value.data.clone())
 
     def get_wy(self) -> torch.Tensor:
-        return self.out.detach().clone()
+        return self._param("out").data.clone()
 
     def set_wy(self, value: torch.Tensor) -> None:
-        setattr(self, "out", nn.Parameter(value))
+        self._parameters["out"] = nn.Parameter(value)      # no copy, like the reference
 
-    # -- forward -----------------------------------------------------------------------------------
+    # -- recurrence: ONE fused [D+H, 4H] projection per timestep ---------------------------------------
     def _stacked(self):
-        wx = torch.cat([getattr(self, f"x2{g}") for g in _GATES], dim=1)      # [D, 4H]
-        wh = torch.cat([getattr(self, f"h2{g}") for g in _GATES], dim=1)      # [H, 4H]
+        wx = torch.cat([self._param("x2" + k) for k in _GATES], dim=1)      # [D, 4H]
+        wh = torch.cat([self._param("h2" + k) for k in _GATES], dim=1)      # [H, 4H]
         return wx, wh
+
+    def _unroll(self, x: torch.Tensor, c_prev: torch.Tensor, h_prev: torch.Tensor):
+        """Yields (t, i, f, g, o, c, h) for t = 1..T starting from (c_prev, h_prev), each [N, H]."""
+        if x.dim() != 3 or x.shape[2] != self.input_size:
+            raise AssertionError(f"expected x of shape [N, T, {self.input_size}], got {tuple(x.shape)}")
+        wx, wh = self._stacked()
+        width = self.hidden_size
+        for t in range(1, x.shape[1] + 1):
+            z = x[:, t - 1] @ wx + h_prev @ wh
+            gate_i = torch.sigmoid(z[:, :width])
+            gate_f = torch.sigmoid(z[:, width:2 * width])
+            gate_g = torch.tanh(z[:, 2 * width:3 * width])
+            gate_o = torch.sigmoid(z[:, 3 * width:])
+            c_prev = gate_f * c_prev + gate_i * gate_g
+            h_prev = gate_o * torch.tanh(c_prev)
+            yield t, gate_i, gate_f, gate_g, gate_o, c_prev, h_prev
 
     def forward(self, x: torch.Tensor, c: Optional[torch.Tensor] = None, h: Optional[torch.Tensor] = None):
         if self.with_grad:
@@ -63,36 +82,28 @@ class LSTM(nn.Module):
         return self.init_gate_variables(x, c, h)["a"]
 
     def grad_forward(self, x: torch.Tensor, c: Optional[torch.Tensor], h: Optional[torch.Tensor]) -> torch.Tensor:
-        assert x.size(2) == self.input_size
-        batch, seq_len, _ = x.size()
-        hs = self.hidden_size
-        c = x.new_zeros(batch, hs) if c is None else c
-        h = x.new_zeros(batch, hs) if h is None else h
-        wx, wh = self._stacked()
-        for t in range(seq_len):
-            zi, zf, zg, zo = (x[:, t, :] @ wx + h @ wh).split(hs, dim=1)
-            c = torch.sigmoid(zf) * c + torch.sigmoid(zi) * torch.tanh(zg)
-            h = torch.sigmoid(zo) * torch.tanh(c)
-        return h @ self.out
+        """Differentiable prediction from [N, H] initial states (reference :48-63)."""
+        zeros = x.new_zeros(x.shape[0], self.hidden_size)
+        last = zeros if h is None else h
+        for *_, last in self._unroll(x, zeros if c is None else c, last):
+            pass
+        return last @ self._param("out")
 
     def init_gate_variables(self, x: torch.Tensor, c: Optional[torch.Tensor] = None,
                             h: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        """State tensors [N, T+1, H] with slot 0 zero, plus a = h_T @ out (reference :65-88)."""
-        assert x.size(2) == self.input_size
-        batch, seq_len, _ = x.size()
-        hs = self.hidden_size
-        shape = (batch, seq_len + 1, hs)
-        st = {k: x.new_zeros(shape) for k in ("i", "f", "g", "o")}
-        st["c"] = x.new_zeros(shape) if c is None else c
-        st["h"] = x.new_zeros(shape) if h is None else h
-        wx, wh = self._stacked()
-        for t in range(1, seq_len + 1):
-            zi, zf, zg, zo = (x[:, t - 1, :] @ wx + st["h"][:, t - 1, :] @ wh).split(hs, dim=1)
-            st["i"][:, t, :] = torch.sigmoid(zi)
-            st["f"][:, t, :] = torch.sigmoid(zf)
-            st["g"][:, t, :] = torch.tanh(zg)
-            st["o"][:, t, :] = torch.sigmoid(zo)
-            st["c"][:, t, :] = st["f"][:, t, :] * st["c"][:, t - 1, :] + st["i"][:, t, :] * st["g"][:, t, :]
-            st["h"][:, t, :] = st["o"][:, t, :] * torch.tanh(st["c"][:, t, :])
-        st["a"] = st["h"][:, seq_len, :] @ self.out
+        """State tensors [N, T+1, H] with slot 0 zero, plus a = h_T @ out (reference :65-88).
+
+        Caller-provided c / h ([N, T+1, H]) are filled in place and their slot 0 is the initial state.
+        """
+        full = (x.shape[0], x.shape[1] + 1, self.hidden_size)
+        names = ("i", "f", "g", "o", "c", "h")
+        st = {k: x.new_zeros(full) for k in names}
+        if c is not None:
+            st["c"] = c
+        if h is not None:
+            st["h"] = h
+        for t, *values in self._unroll(x, st["c"][:, 0], st["h"][:, 0]):
+            for k, v in zip(names, values):
+                st[k][:, t] = v
+        st["a"] = st["h"][:, -1] @ self._param("out")
         return st

@@ -181,7 +181,20 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
   const int H = p.H;
   const int64_t ldn = p.ldn;
   const Rho rho = p.rho;
-  const int64_t soff = (int64_t)tl * p.s_tstride;
+  // Addressing: every access is base pointer + 32-bit element offset (one IMAD.WIDE.U32 instead of 64-bit index
+  // arithmetic per access; the epilogue is bound by instruction issue, and integer index arithmetic was 40 % of it).
+  // The offsets are relative to the first slab of the launch and stay below 2^32 for any tensor that fits the GPU
+  // (checked on the host, gate_gemm_tc): row0 = this thread's sample in unit j0 of the tile's timestep, then one
+  // 32-bit step per unit.  zstore / scratch are [4][H][zT or tc][ldn]: the gate stride goes into the (uniform) base.
+  const uint32_t ldn32 = (uint32_t)ldn;
+  const uint32_t row0 = (uint32_t)((int64_t)tl * p.s_tstride + (int64_t)j0 * ldn + n);
+  const uint32_t dh0 = (uint32_t)((int64_t)j0 * ldn + n);                                 // lambda_h has the t = T slab only
+  const uint32_t zrow0 = (uint32_t)(((int64_t)j0 * p.zT + p.zt0 + tl) * ldn + n);
+  const uint32_t zstep = (uint32_t)((int64_t)p.zT * ldn);
+  const int64_t zgate = (int64_t)H * p.zT * ldn;
+  const uint32_t srow0 = (uint32_t)(((int64_t)j0 * p.tc + tl) * ldn + n);
+  const uint32_t sstep = (uint32_t)((int64_t)p.tc * ldn);
+  const int64_t sgate = (int64_t)H * p.tc * ldn;
     // The epilogue is latency-bound if each unit waits for its own loads (measured: ~3x the MMA time of a tile):
     // every batch of EB units first issues ALL its global loads, then computes, then stores, so ~13*EB loads are
     // in flight per thread.  Loads use the streaming path (each state entry is touched once per launch).
@@ -200,16 +213,21 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
       }
 #pragma unroll
       for (int eb = 0; eb < 8; eb += EB) {
-        int64_t off[EB];
+        uint32_t off[EB], zoff[EB], soffs[EB];
 #pragma unroll
-        for (int e = 0; e < EB; ++e) off[e] = soff + (int64_t)(j0 + jb + eb + e) * ldn + n;
+        for (int e = 0; e < EB; ++e) {
+          const uint32_t ju = (uint32_t)(jb + eb + e);          // unit within the tile
+          off[e] = row0 + ju * ldn32;
+          zoff[e] = zrow0 + ju * zstep;
+          soffs[e] = srow0 + ju * sstep;
+        }
 
         if (MODE == GG_RAWZ) {
 #pragma unroll
           for (int e = 0; e < EB; ++e)
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              __stcs(p.scratch + (((int64_t)g * H + (j0 + jb + eb + e)) * p.tc + tl) * ldn + n, z[g][eb + e]);
+              __stcs(p.scratch + g * sgate + soffs[e], z[g][eb + e]);
         }
         if (MODE == GG_FORWARD) {
           float cp[EB];
@@ -221,7 +239,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             if (p.zstore) {
 #pragma unroll
               for (int g = 0; g < 4; ++g)
-                __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, z[g][eb + e]);
+                __stcs(p.zstore + g * zgate + zoff[e], z[g][eb + e]);
             }
             if (p.gate[0]) __stcs(p.gate[0] + off[e], r.i);
             if (p.gate[1]) __stcs(p.gate[1] + off[e], r.f);
@@ -247,7 +265,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
               in[6][e] = __ldcs(p.c_prev + off[e]);
 #pragma unroll
               for (int q = 0; q < 5; ++q) in[7 + q][e] = __ldcs(p.dual[q] + off[e]);
-              in[12][e] = p.last ? __ldcs(p.dual_h + (int64_t)(j0 + jb + eb + e) * ldn + n) : 0.f;
+              in[12][e] = p.last ? __ldcs(p.dual_h + (dh0 + (uint32_t)(jb + eb + e) * ldn32)) : 0.f;
             }
           }
           // NOTE on the never-taken branches (p.last is 0 or 1): they only shape ptxas' schedule.  Putting the loads of a
@@ -278,7 +296,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             if (p.zstore) {
 #pragma unroll
               for (int g = 0; g < 4; ++g)
-                __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, z[g][eb + e]);
+                __stcs(p.zstore + g * zgate + zoff[e], z[g][eb + e]);
             }
             if (ok) { msum[0] += r.prim_sq; msum[1] += r.dual_sq; msum[2] += r.penalty; }
           }
@@ -298,7 +316,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
                 lam[g][e] = __ldcs(p.dual[g] + off[e]);
                 gv[g][e] = __ldcs(p.gate[g] + off[e]);
                 zold[g][e] = p.z_accumulate
-                    ? __ldcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n) : 0.f;
+                    ? __ldcs(p.zstore + g * zgate + zoff[e]) : 0.f;
               }
           }
 #pragma unroll
@@ -319,13 +337,12 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int64_t so = (((int64_t)g * H + (j0 + jb + eb + e)) * p.tc + tl) * ldn + n;
-              if (p.zstore) __stcs(p.zstore + (((int64_t)g * H + (j0 + jb + eb + e)) * p.zT + p.zt0 + tl) * ldn + n, zz[g]);
+              if (p.zstore) __stcs(p.zstore + g * zgate + zoff[e], zz[g]);
               if (p.r16_hi) {                                // h-phase: fp16 pair for the fp16 A^T R GEMM
-                split_f16(rv[g] * r_scale, p.r16_hi + so, p.r16_lo + so);
+                split_f16(rv[g] * r_scale, p.r16_hi + g * sgate + soffs[e], p.r16_lo + g * sgate + soffs[e]);
               } else {
-                p.scratch[so] = rv[g];                       // read right back by the A^T R GEMM: keep in L2
-                if (p.scratch_q) p.scratch_q[so] = tf32_lo(rv[g]);
+                *(p.scratch + g * sgate + soffs[e]) = rv[g];   // read right back by the A^T R GEMM: keep in L2
+                if (p.scratch_q) *(p.scratch_q + g * sgate + soffs[e]) = tf32_lo(rv[g]);
               }
             }
           }
@@ -356,7 +373,9 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[4 * P_EPI_WARPS];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells ptxas it is warp-uniform, so the role branches below are uniform branches and
+  // the epilogue keeps its pointers / memory descriptors on the uniform datapath (no R2UR round trips per load)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int D = p.D, H = p.H;
   const int nkx = (D + BK - 1) / BK;
   const int nkb = rng.kb_end - rng.kb_begin;
@@ -691,12 +710,18 @@ int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, 
 
 }  // namespace
 
-bool tc_eligible(const admm_problem* p) {
-  return p->H % 64 == 0 && p->H >= 64 && p->ldn % 128 == 0 && get_encode() != nullptr;
+namespace {
+// shape rules of the tensor-core path; the last one keeps the epilogue's 32-bit element offsets valid (a state tensor
+// of 2^32 floats is 17 GB, eleven of them exceed the GPU's memory, so this never binds on a B200)
+bool tc_shape_ok(const admm_problem* p) {
+  return p->H % 64 == 0 && p->H >= 64 && p->ldn % 128 == 0 && (int64_t)(p->T + 1) * p->H * p->ldn < ((int64_t)1 << 32);
 }
+}  // namespace
+
+bool tc_eligible(const admm_problem* p) { return tc_shape_ok(p) && get_encode() != nullptr; }
 
 int64_t tc_workspace_bytes(const admm_problem* p) {
-  if (!(p->H % 64 == 0 && p->H >= 64 && p->ldn % 128 == 0)) return 0;
+  if (!tc_shape_ok(p)) return 0;
   return ws_layout(p).total * 4;
 }
 
@@ -774,6 +799,12 @@ void tc_h16(const admm_problem* p, __half** hi, __half** lo) {
 int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int tc, cudaStream_t st) {
   GateGemmArgs a = a_in;
   TcMaps maps;
+  // the epilogue addresses state, zstore and scratch with 32-bit element offsets from the launch's first slab
+  if ((int64_t)(p->T + 1) * p->H * p->ldn >= ((int64_t)1 << 32) || (int64_t)tc * p->H * p->ldn >= ((int64_t)1 << 32)) {
+    set_error("gate_gemm_tc: a state tensor of %lld elements exceeds the 32-bit offsets of the epilogue",
+              (long long)((int64_t)(p->T + 1) * p->H * p->ldn));
+    return ADMM_EINVAL;
+  }
   // the "gradient" operand slot holds G of the probed weight, or, for the zstore refresh of the h-phase, W_new - W_old of x2g
   const bool z_refresh = (mode == GG_GRAD && a.z_accumulate);
   int rc = get_maps(p, z_refresh ? ADMM_SRC_X : a.src, &maps);

@@ -47,6 +47,7 @@ struct GateGemmArgs {
   const unsigned* r_bound;
   __half* r16_hi;
   __half* r16_lo;
+  int32_t epi_prefetch;  // tensor-core path, SWEEP: L2 prefetch of the epilogue's next batch of units (set by gate_gemm_tc)
 };
 
 int gate_gemm_simt(int mode, const GateGemmArgs& a, int tc, cudaStream_t st);

@@ -171,6 +171,20 @@ __device__ __forceinline__ void store_h16(__half* hi, __half* lo, float h) {
   split_f16(h * (float)(1 << SCALE_H), hi, lo);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// L2 prefetch of the twelve state entries the SWEEP epilogue loads for the unit at 32-bit offset o (lane == sample: one
+// 128-byte line per warp and stream).  A prefetch holds no register, so it adds the memory-level parallelism the register
+// file cannot: issued one batch of units ahead, the loads of the next batch find their lines in L2 (sweep kernel
+// 0.61 -> 0.52 ms per cfg3 launch).  Not used by the GRAD epilogue, where it measured slower.
+__device__ __forceinline__ void sweep_prefetch(const GateGemmArgs& p, uint32_t o) {
+#pragma unroll
+  for (int q = 0; q < 6; ++q) prefetch_l2(p.gate[q] + o);
+  prefetch_l2(p.c_prev + o);
+#pragma unroll
+  for (int q = 0; q < 5; ++q) prefetch_l2(p.dual[q] + o);
+}
+
 // Epilogue of one tile for the units [u_begin, u_end) (multiples of 8) of the calling warp's 32 sample rows: reads the
 // accumulator columns from TMEM (t_row = TMEM address of the warp's lane quarter, accumulator buffer included) and
 // applies the closed forms of admm_math.cuh with coalesced (lane == sample) global accesses.
@@ -266,6 +280,10 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
 #pragma unroll
               for (int q = 0; q < 5; ++q) in[7 + q][e] = __ldcs(p.dual[q] + off[e]);
               in[12][e] = p.last ? __ldcs(p.dual_h + (dh0 + (uint32_t)(jb + eb + e) * ldn32)) : 0.f;
+            }
+            if (p.epi_prefetch && jb + eb + EB < u_end) {
+#pragma unroll
+              for (int e = 0; e < EB; ++e) sweep_prefetch(p, off[e] + EB * ldn32);
             }
           }
           // NOTE on the never-taken branches (p.last is 0 or 1): they only shape ptxas' schedule.  Putting the loads of a
@@ -820,6 +838,11 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   }
   const TcMeta* meta = ws_meta(p);
   a.acc_scale = z_refresh ? &meta->scale_d : &meta->scale_z;
+  static const int epi_prefetch = [] {          // on unless ADMM_EPI_PREFETCH=0 (A/B switch for measurements)
+    const char* e = getenv("ADMM_EPI_PREFETCH");
+    return e ? atoi(e) : 1;
+  }();
+  a.epi_prefetch = epi_prefetch;
   const int nkx = (p->D + BK - 1) / BK, nkh = (p->H + BK - 1) / BK;
   const TcRange full{0, nkx + nkh, 0};
   switch (mode) {

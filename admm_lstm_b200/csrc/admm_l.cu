@@ -5,7 +5,7 @@
 //  * weight phase: the residual -z_t + x_t W + h_{t-1} U - lambda_t/rho is linear in W and U (admm_lstm.py:107-163), so
 //    the eight updates need only Gram / right-hand-side sums over samples x timesteps.  They come from ONE packing pass
 //    (V_g = z_g + lambda_g/rho and h_{t-1}, five row groups) and two runs of the A^T R reduction GEMM of the main path
-//    (tcgen05 3xTF32, fp64 accumulation across chunks); the reference re-runs 2T GEMMs per backtracking probe.
+//    (tcgen05 on fp16 pairs, fp64 accumulation across chunks); the reference re-runs 2T GEMMs per backtracking probe.
 //  * sweep: one gate GEMM per timestep (the reference recomputes x W + h U eight times per timestep) and three
 //    elementwise kernels separated by the algorithm's own global reductions (torch.max in update_z / update_zg /
 //    update_c and fro_qua(o), admm_lstm.py:168,179,225,230), which are also where sample shards must exchange scalars.

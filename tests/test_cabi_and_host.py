@@ -54,6 +54,28 @@ def test_no_cpu_fallback():
     assert b"no CPU path" in lib.admm_last_error()
 
 
+def test_tensor_core_shape_rules():
+    """admm_tc_workspace_bytes (pure host arithmetic): the tensor-core path needs H % 64 == 0, ldn % 128 == 0 and state
+    tensors below 2^32 elements (its epilogue addresses them with 32-bit offsets); otherwise 0 -> CUDA-core path."""
+    _build()
+    from admm_lstm_b200 import _lib
+    lib = _lib.load()
+
+    def ws(T, D, H, ldn):
+        p = _lib.Problem()
+        p.n = p.n_global = ldn
+        p.ldn = ldn
+        p.T, p.D, p.H, p.O = T, D, H, 1
+        return int(lib.admm_tc_workspace_bytes(ctypes.byref(p)))
+
+    assert ws(128, 64, 1024, 16384) > 0                   # the bench shape
+    assert ws(10, 1, 10, 4224) == 0                       # GoogleStock: H % 64 != 0
+    assert ws(128, 64, 1024, 16384 + 64) == 0             # ldn not a multiple of 128
+    assert (128 + 1) * 1024 * 32512 < 2 ** 32 <= (128 + 1) * 1024 * 32640
+    assert ws(128, 64, 1024, 32512) > 0
+    assert ws(128, 64, 1024, 32640) == 0                  # 129 * 1024 * 32640 elements >= 2^32
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "admm_lstm_b200")):
         for f in files:

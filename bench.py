@@ -88,6 +88,9 @@ def time_oracle(workload, steps, warmup, threads=None):
     from oracle.admm_oracle import OracleADMM
     from admm_lstm_b200.parameters import example_parameter_dictionary as epd
     n_gpu, t, d, h, o, pname, cpu_n, cls = WORKLOADS[workload]
+    # keep a long --steps run within a few minutes: the sample shrinks beyond 8 iterations (CPU throughput is flat in N)
+    if steps + warmup > 8:
+        cpu_n = max(32, cpu_n * 8 // (steps + warmup) // 32 * 32)
     x, y, w = make_data(cpu_n, t, d, h, o, 0, cls)
     ora = OracleADMM(w, x, y, bench_params(pname, cpu_n, h), variant="admm")
     for _ in range(warmup):

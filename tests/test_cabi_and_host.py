@@ -86,14 +86,16 @@ def test_product_never_imports_oracle():
         assert "import oracle" not in open(os.path.join(ROOT, f)).read()
 
 
+@pytest.mark.parametrize("w_scale", [1.0, 60.0])
 @pytest.mark.parametrize("variant", ["admm", "no_dual_y"])
-def test_point_math_matches_oracle(variant):
-    """csrc/admm_math.cuh compiled for the host == oracle's sequential per-function updates."""
+def test_point_math_matches_oracle(variant, w_scale):
+    """csrc/admm_math.cuh compiled for the host == oracle's sequential per-function updates.  w_scale = 60 drives the
+    pre-activations deep into saturation (sigmoid == 0 or 1, tanh == +-1, derivatives == 0 in fp32)."""
     from oracle.admm_oracle import OracleADMM
     _, host = _build()
     lib = ctypes.CDLL(host)
     rec = load(f"fn_{variant}.npz")
-    base_w = {k: rec[f"base_w_{k}"] for k in WKEYS}
+    base_w = {k: (rec[f"base_w_{k}"] * np.float32(w_scale)).astype(np.float32) for k in WKEYS}
     st = state_from(rec, "base_")
     T = rec["x"].shape[1]
     fp = ctypes.POINTER(ctypes.c_float)
@@ -122,6 +124,10 @@ def test_point_math_matches_oracle(variant):
                 ora.update_dual_ifgo(k, t)
             ora.update_dual_c(t)
             shape = g["i"][:, t, :].shape
+            assert np.isfinite(out).all()
+            if w_scale > 1:
+                zmax = max(float(np.abs(r).max()) for r in rows[:4])
+                assert zmax > 30, zmax                 # the case really is saturated
             for q, k in enumerate("ifgoc" + ("h" if t < T else "")):
                 np.testing.assert_allclose(out[q].reshape(shape), g[k][:, t, :], rtol=3e-5, atol=3e-6, err_msg=f"{k}@{t}")
             for q, k in enumerate("ifgoc"):

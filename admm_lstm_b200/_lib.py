@@ -89,6 +89,8 @@ SIGNATURES = {
     "admm_tc_refresh": (C.c_int, [PP, C.c_int, vp]),
     "admm_debug_preact": (C.c_int, [PP, C.c_int, vp, C.c_int, vp]),
     "admm_launch_count": (C.c_int64, [C.c_int]),
+    "admm_kernel_timing": (C.c_int, [C.c_int]),
+    "admm_kernel_timing_report": (C.c_int64, [C.c_char_p, C.c_int64]),
     # ADMM-LSTM-L
     "admm_l_sizeof_problem": (C.c_int, []),
     "admm_l_forward_t": (C.c_int, [LPP, C.c_int, vp, vp, vp]),

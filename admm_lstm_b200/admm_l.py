@@ -353,7 +353,7 @@ def admm_l_demo(num_epochs, n_hiddens, train_x, train_y, test_x, test_y, save=Fa
         loss_train.append(mse(opt.predict(train_x), train_y_d))
         loss_test.append(mse(opt.predict(test_x), test_y_d))
         info(f"ADMM-LSTM-L: k = {k + 1}, loss train = {loss_train[-1]}, loss test = {loss_test[-1]}")
-    if save:
+    if save and opt.comm.rank == 0:                                           # replicated weights: one writer
         os.makedirs("SAVED_MODELS", exist_ok=True)
         torch.save(opt.model().cpu(), os.path.join("SAVED_MODELS", "ADMM-LSTM-L.pt"))
     return {"name": "ADMM-LSTM-L", "train_loss": loss_train, "val_loss": loss_test}

@@ -42,16 +42,31 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _source_hash(deps) -> str:
+    """Content hash of every source the library is built from (+ the flags): what decides whether a shipped .so is
+    current -- file times do not survive a snapshot copy."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    for d in sorted(os.path.abspath(x) for x in deps):
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     deps = _deps()
-    if not force and not _stale(LIB, deps):
-        return LIB
+    stamp, want = LIB + ".srchash", _source_hash(deps)
+    have = open(stamp).read().strip() if os.path.exists(stamp) else None
+    if not force and os.path.exists(LIB) and have == want:
+        return LIB                      # built from exactly these sources
+    if not force and have is None and not _stale(LIB, deps) and shutil.which("nvcc") is None:
+        return LIB                      # no stamp, no compiler: the shipped library is all there is
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        if force or _stale(obj, deps):
+        if force or have != want or _stale(obj, deps):
             cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 cmd.insert(-4, "-Xptxas")
@@ -68,6 +83,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(want + "\n")
     return LIB
 
 

@@ -469,6 +469,7 @@ int admm_l_forward_t(const admm_l_problem* lp, int s, float* scratch, float* nex
   if (s == 1 && (rc = reset_bound(lp, st))) return rc;
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch, next_max);
+  KernelScope ks_("l_forward_kernel", st);
   l_forward_kernel<<<ew_grid1(k.ldn, k.H), NT, 0, st>>>(k);
   count_launch();
   return check_launch("l_forward");
@@ -502,7 +503,10 @@ int admm_l_sums(const admm_l_problem* lp, int t0, int tc, float* scratch, double
     k.r16_lo = reinterpret_cast<__half*>(scratch + half);
     k.r_bound = tc_r_bound(&b);
   }
-  l_pack_kernel<<<ew_grid2(b.ldn, b.H * tc), NT, 0, st>>>(k);
+  {
+    KernelScope ks_("l_pack_kernel", st);
+    l_pack_kernel<<<ew_grid2(b.ldn, b.H * tc), NT, 0, st>>>(k);
+  }
   count_launch();
   if ((rc = check_launch("l_pack"))) return rc;
   AtrArgs r;
@@ -551,6 +555,7 @@ int admm_l_sums_last(const admm_l_problem* lp, double* s_tt, double* p_t, void* 
   r.g_acc = s_tt;
   rc = atr_simt(r, st);                 // one [H,H] Gram of a single timestep: CUDA-core reduction
   if (rc) return rc;
+  KernelScope ks_("l_pt_kernel", st);
   l_pt_kernel<<<b.H, NT, 0, st>>>(b.gate[5] + (int64_t)b.T * slab, b.a, b.dual_y, lp->hp.rho11, b.n, b.ldn, p_t);
   count_launch();
   return check_launch("l_pt");
@@ -564,6 +569,7 @@ int admm_l_sweep_gates(const admm_l_problem* lp, int s, float* scratch, float* r
   if (s == 1 && (rc = reset_bound(lp, st))) return rc;       // the sweep re-measures the bound of the next packing pass
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch);
+  KernelScope ks_("l_gates_kernel", st);
   l_gates_kernel<<<ew_grid1(k.ldn, k.H), NT, 0, st>>>(k, red_max, red_sum);
   count_launch();
   return check_launch("l_gates");
@@ -576,6 +582,7 @@ int admm_l_sweep_cell(const admm_l_problem* lp, int s, const float* scratch, con
   ADMM_REQUIRE(s >= 1 && s <= lp->base.T && scratch && red_max && red_sum && next_max, "admm_l_sweep_cell: bad arguments");
   const LSlot k = make_slot(lp, s, scratch, next_max);
   const dim3 grid = ew_grid1(k.ldn, k.H);
+  KernelScope ks_("l_cell_kernel", (cudaStream_t)stream);
   if (s == lp->base.T) l_cell_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
   else l_cell_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(k, red_max, red_sum);
   count_launch();
@@ -592,6 +599,7 @@ int admm_l_last(const admm_l_problem* lp, const float* theta_h, float* tmp, cons
   const LSlot k = make_slot(lp, b.T, scratch, next_max);
   const unsigned nb = (unsigned)((b.n + NT - 1) / NT);
   const dim3 grid = ew_grid1(k.ldn, k.H);
+  KernelScope ks_("l_last kernels (form10, last_h, last_a, duals)", st);
   l_form10_kernel<<<nb, NT, 0, st>>>(k.gate[5], b.wy, b.a, b.dual_y, lp->hp.rho11, b.n, b.ldn, b.H, tmp);
   l_last_h_kernel<<<grid, NT, 0, st>>>(k, b.wy, tmp, theta_h);
   const float a_den = (float)(2.0 / (double)lp->hp.n_norm + (double)lp->hp.rho11);

@@ -141,6 +141,7 @@ int launch(const AtrArgs& a, cudaStream_t st) {
   const int cpc = (n_chunks + splits - 1) / splits;
   splits = (n_chunks + cpc - 1) / cpc;
   dim3 grid((a.K + KT - 1) / KT, (rows + CT - 1) / CT, splits);
+  KernelScope ks_("atr_simt_kernel", st);
   atr_simt_kernel<KT, CT, MK, MC><<<grid, NT, 0, st>>>(a, cpc, n_chunks);
   count_launch();
   return check_launch("atr_simt");

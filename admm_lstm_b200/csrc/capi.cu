@@ -7,6 +7,10 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "gate_gemm.h"
@@ -25,6 +29,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// ---- per-kernel CUDA-event timing (KernelScope, common.cuh) ------------------------------------------------------
+namespace {
+struct KtRec { const char* name; cudaEvent_t e0, e1; };
+std::atomic<int> g_kt_on{0};
+std::mutex g_kt_mu;
+std::vector<KtRec> g_kt;
+thread_local int g_kt_depth = 0;
+}  // namespace
+
+KernelScope::KernelScope(const char* name, cudaStream_t st) : name_(name), st_(st), e0_(nullptr) {
+  if (!g_kt_on.load(std::memory_order_relaxed)) return;
+  if (g_kt_depth++ > 0) return;                     // nested scopes: the outermost one owns the interval
+  if (cudaEventCreate(&e0_) != cudaSuccess) { e0_ = nullptr; return; }
+  cudaEventRecord(e0_, st_);
+}
+KernelScope::~KernelScope() {
+  if (!g_kt_on.load(std::memory_order_relaxed) && !e0_) return;
+  if (g_kt_depth > 0) --g_kt_depth;
+  if (!e0_) return;
+  cudaEvent_t e1;
+  if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0_); return; }
+  cudaEventRecord(e1, st_);
+  std::lock_guard<std::mutex> lk(g_kt_mu);
+  g_kt.push_back(KtRec{name_, e0_, e1});
+}
+
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -99,6 +129,46 @@ int admm_sizeof_problem(void) { return (int)sizeof(admm_problem); }
 int admm_device_ok(void) { return device_ok(); }
 int64_t admm_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int admm_kernel_timing(int enable) {
+  const int was = g_kt_on.exchange(enable ? 1 : 0);
+  if (enable && !was) {
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    for (auto& r : g_kt) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_kt.clear();
+  }
+  return was;
+}
+
+int64_t admm_kernel_timing_report(char* buf, int64_t len) {
+  if (!buf || len <= 0) return ADMM_EINVAL;
+  std::map<std::string, std::pair<int64_t, double>> agg;
+  std::vector<std::string> order;
+  {
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    for (auto& r : g_kt) {
+      if (cudaEventSynchronize(r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+      auto it = agg.find(r.name);
+      if (it == agg.end()) { order.push_back(r.name); it = agg.emplace(r.name, std::make_pair((int64_t)0, 0.0)).first; }
+      it->second.first += 1;
+      it->second.second += ms;
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    g_kt.clear();
+  }
+  std::string out;
+  char line[256];
+  for (auto& name : order) {
+    snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", name.c_str(), (long long)agg[name].first, agg[name].second);
+    out += line;
+  }
+  if ((int64_t)out.size() + 1 > len) { set_error("admm_kernel_timing_report: buffer of %lld bytes too small", (long long)len); return ADMM_EINVAL; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int64_t)out.size();
 }
 
 int admm_forward_t(const admm_problem* p, int t, void* stream) {

@@ -13,6 +13,20 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);
 
+// Per-kernel CUDA-event timing (admm_kernel_timing in the C ABI; bench.py's per-kernel roofline table).  A KernelScope placed
+// before a launch records an event pair around everything launched on `st` during its lifetime when timing is enabled;
+// disabled (the default) it costs one relaxed atomic load.
+struct KernelScope {
+  KernelScope(const char* name, cudaStream_t st);
+  ~KernelScope();
+  KernelScope(const KernelScope&) = delete;
+  KernelScope& operator=(const KernelScope&) = delete;
+ private:
+  const char* name_;
+  cudaStream_t st_;
+  cudaEvent_t e0_;
+};
+
 #define ADMM_REQUIRE(cond, ...)          \
   do {                                   \
     if (!(cond)) {                       \

@@ -301,6 +301,7 @@ int launch(const GateGemmArgs& a, int tc, cudaStream_t st) {
   constexpr int BM = 16 * TM;
   // all ldn rows, ghosts included: the scratch rows the reduction GEMM reads must all be written (ghost R = 0)
   dim3 grid((unsigned)(a.ldn / BM), (unsigned)((a.H + BJ - 1) / BJ), (unsigned)tc);
+  KernelScope ks_("gate_gemm_simt_kernel", st);
   gate_gemm_simt_kernel<MODE, TM><<<grid, NTHREADS, 0, st>>>(a);
   count_launch();
   return check_launch("gate_gemm_simt");

@@ -705,8 +705,9 @@ int get_maps(const admm_problem* p, int grad_src, TcMaps* out) {
 
 template <int MODE>
 int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, int slab0, int tc, const TcRange& rng,
-              cudaStream_t st) {
+              cudaStream_t st, const char* label) {
   using C = Cfg;
+  KernelScope ks_(label, st);
   static bool configured_p = false;
   if (!configured_p) {
     cudaFuncSetAttribute(gate_gemm_tc_persistent<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
@@ -747,6 +748,7 @@ namespace {
 // max |a - b| (b may be null) -> *slot, then the fp16 pair of the scaled values
 int prep_operand(int kind, const float* a, const float* b, __half* hi, __half* lo, int64_t n, TcMeta* meta, unsigned* slot,
                  cudaStream_t st) {
+  KernelScope ks_("tc_prep_operand", st);
   if (slot) {
     if (cudaMemsetAsync(slot, 0, sizeof(unsigned), st) != cudaSuccess) return check_launch("prep memset");
     absmax_kernel<<<prep_grid(n), 256, 0, st>>>(a, b, n, slot);
@@ -762,6 +764,7 @@ int tc_refresh_weights(const admm_problem* p, cudaStream_t st) {
   const WsLayout w = ws_layout(p);
   TcMeta* meta = ws_meta(p);
   const int64_t nx = 4LL * p->D * p->H, nh = 4LL * p->H * p->H;
+  KernelScope ks_("tc_refresh_weights", st);
   // both maxima first: the common accumulator scale depends on both
   if (cudaMemsetAsync(&meta->max_wx, 0, 2 * sizeof(unsigned), st) != cudaSuccess) return check_launch("prep memset");
   absmax_kernel<<<prep_grid(nx), 256, 0, st>>>(p->wx, nullptr, nx, &meta->max_wx);
@@ -777,6 +780,7 @@ int tc_refresh_inputs(const admm_problem* p, cudaStream_t st) {
   float* ws = (float*)p->tc_ws;
   TcMeta* meta = ws_meta(p);
   const int64_t nx = (int64_t)p->T * p->D * p->ldn;
+  KernelScope ks_("tc_refresh_inputs", st);
   split_trunc_kernel<<<(unsigned)((nx / 4 + 255) / 256 + 1), 256, 0, st>>>(p->x, ws + w.x_lo, nx);
   count_launch();
   int rc = prep_operand(PREP_X, p->x, nullptr, ws_half(p, w.x16_hi), ws_half(p, w.x16_lo), nx, meta, &meta->max_x, st);
@@ -846,24 +850,24 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   const int nkx = (p->D + BK - 1) / BK, nkh = (p->H + BK - 1) / BK;
   const TcRange full{0, nkx + nkh, 0};
   switch (mode) {
-    case GG_FORWARD: return launch_tc<GG_FORWARD>(p, a, maps, slab0, tc, full, st);
-    case GG_SWEEP: return launch_tc<GG_SWEEP>(p, a, maps, slab0, tc, full, st);
+    case GG_FORWARD: return launch_tc<GG_FORWARD>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<FORWARD>");
+    case GG_SWEEP: return launch_tc<GG_SWEEP>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<SWEEP>");
     case GG_GRAD:
-      if (z_refresh) return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, TcRange{0, nkx, 1}, st);
-      return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, full, st);
-    case GG_RAWZ: return launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st);
+      if (z_refresh) return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, TcRange{0, nkx, 1}, st, "gate_gemm_tc<GRAD:z+=x*dW>");
+      return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<GRAD:full>");
+    case GG_RAWZ: return launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<RAWZ:z>");
     case GG_PROBE: {
       // Z0 = x W + h U, then Q = A_src G: two launches of the same kernel (each keeps the 64-unit tile and
       // two resident CTAs per SM; a fused Z0|Q tile needs all 512 TMEM columns and halves the tile width)
       if (!a.zstore) {
-        rc = launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st);
+        rc = launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<RAWZ:z>");
         if (rc) return rc;
       }
       GateGemmArgs q = a;
       q.scratch = a.scratch_q;
       q.acc_scale = &meta->scale_q;
       const TcRange qr = (a.src == ADMM_SRC_X) ? TcRange{0, nkx, 1} : TcRange{nkx, nkx + nkh, 1};
-      return launch_tc<GG_RAWZ>(p, q, maps, slab0, tc, qr, st);
+      return launch_tc<GG_RAWZ>(p, q, maps, slab0, tc, qr, st, a.src == ADMM_SRC_X ? "gate_gemm_tc<RAWZ:Q=x*G>" : "gate_gemm_tc<RAWZ:Q=h*G>");
     }
   }
   set_error("gate_gemm_tc: bad mode %d", mode);
@@ -1060,6 +1064,8 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
   splits = (n_chunks + cpc - 1) / cpc;
   dim3 grid((unsigned)(rows / 128), (unsigned)((a.K + NT_ - 1) / NT_), (unsigned)splits);
   const unsigned* a_max = src_is_x ? &ws_meta(p)->max_x : nullptr;
+  KernelScope ks_(F16 ? (NT_ == 256 ? "atr_tc<256,f16>" : NT_ == 128 ? "atr_tc<128,f16>" : "atr_tc<64,f16>")
+                      : (NT_ == 256 ? "atr_tc<256,tf32>" : NT_ == 128 ? "atr_tc<128,tf32>" : "atr_tc<64,tf32>"), st);
   atr_tc_kernel<NT_, F16><<<grid, ATR_THREADS, SMEM, st>>>(m, a.g_acc, a.K, rpg, a.tc, a.ldn, slab0, cpc, n_chunks, splits > 1,
                                                            a.r_bound, a_max);
   count_launch();

@@ -67,6 +67,7 @@ int grad_from_z(const GradFromZArgs& a, cudaStream_t st) {
   const int n_nb = (int)((a.ldn / 4 + NT - 1) / NT);
   const int64_t items = (int64_t)a.H * a.tc * n_nb;
   const unsigned gx = (unsigned)(items < 148 * 2 ? items : 148 * 2);
+  KernelScope ks_("grad_from_z_kernel", st);
   grad_from_z_kernel<<<dim3(gx, 4), NT, 0, st>>>(a, n_nb, items);
   count_launch();
   return check_launch("grad_from_z");

@@ -249,6 +249,7 @@ int probe_eval(const ProbeEvalArgs& a, cudaStream_t st) {
   if (nc <= 0 || n_jb <= 0) return ADMM_OK;
   const int64_t n_items = (int64_t)n_nb * n_jb * 4 * a.tc;
   const unsigned grid = (unsigned)(n_items < 148 * 8 ? n_items : 148 * 8);
+  KernelScope ks_("probe_eval_kernel", st);
   if (nc <= 4) launch_probe_eval<4>(a, grid, n_jb, n_nb, n_items, st);
   else if (nc <= 8) launch_probe_eval<8>(a, grid, n_jb, n_nb, n_items, st);
   else if (nc <= 12) launch_probe_eval<12>(a, grid, n_jb, n_nb, n_items, st);
@@ -264,6 +265,7 @@ int probe_moments(const ProbeEvalArgs& a, float* qmax, cudaStream_t st) {
   const int n_jb = (a.H + JB - 1) / JB;
   const int64_t n_items = (int64_t)n_nb * n_jb * 4 * a.tc;
   const unsigned grid = (unsigned)(n_items < 148 * 8 ? n_items : 148 * 8);
+  KernelScope ks_("probe_moments_kernel", st);
   probe_moments_kernel<<<grid, NT, 0, st>>>(a, qmax, n_jb, n_nb, n_items);
   count_launch();
   return check_launch("probe_moments");

@@ -412,38 +412,45 @@ __global__ void weight_apply_kernel(float* w_all, const float* grad_all, const f
 // ------------------------------------------------------------------------------------ launchers
 int launch_wy_grad(const admm_problem& p, double* g_acc, cudaStream_t st) {
   const unsigned blocks = (unsigned)(p.ldn / NT);
+  KernelScope ks_("wy_grad_kernel", st);
   wy_grad_kernel<<<blocks, NT, 0, st>>>(p, g_acc);
   count_launch();
   return check_launch("wy_grad");
 }
 int launch_wy_apply(const admm_problem& p, const double* g_acc, cudaStream_t st) {
   const int tot = p.H * p.O;
+  KernelScope ks_("wy_apply_kernel", st);
   wy_apply_kernel<<<(tot + 255) / 256, 256, 0, st>>>(p, g_acc);
   count_launch();
   return check_launch("wy_apply");
 }
 int launch_last_probe(const admm_problem& p, double* sums, cudaStream_t st) {
+  KernelScope ks_("last_probe_kernel", st);
   last_probe_kernel<<<(unsigned)(p.ldn / NT), NT, 0, st>>>(p, sums);
   count_launch();
   return check_launch("last_probe");
 }
 int launch_last_select(const admm_problem& p, const double* sums, float* theta, cudaStream_t st) {
+  KernelScope ks_("last_select_kernel", st);
   last_select_kernel<<<1, 32, 0, st>>>(p, sums, theta);
   count_launch();
   return check_launch("last_select");
 }
 int launch_last_apply(const admm_problem& p, const float* theta, double* metrics, cudaStream_t st) {
+  KernelScope ks_("last_apply_kernel", st);
   last_apply_kernel<<<(unsigned)(p.ldn / NT), NT, 0, st>>>(p, theta, metrics);
   count_launch();
   return check_launch("last_apply");
 }
 int launch_output(const float* hT, const float* wy, float* a, int64_t ldn, int H, int O, cudaStream_t st) {
+  KernelScope ks_("output_kernel", st);
   output_kernel<<<(unsigned)(ldn / NT), NT, 0, st>>>(hT, wy, a, ldn, H, O);
   count_launch();
   return check_launch("output");
 }
 int launch_weight_finish(const admm_problem& p, int src, const double* g_acc, float* grad, cudaStream_t st) {
   const int64_t per_gate = (int64_t)(src == ADMM_SRC_X ? p.D : p.H) * p.H;
+  KernelScope ks_("weight_finish_kernel", st);
   weight_finish_kernel<<<(unsigned)((4 * per_gate + 255) / 256), 256, 0, st>>>(g_acc, grad, p.hp, per_gate);
   count_launch();
   return check_launch("weight_finish");
@@ -454,12 +461,14 @@ int launch_weight_est(const admm_problem& p, int src, const float* grad, double*
   if (cudaMemsetAsync(est_acc, 0, sizeof(double) * 4 * ADMM_EST_CAND * 2, st) != cudaSuccess) return check_launch("est memset");
   const unsigned nz = (unsigned)((per_gate + 256 * 64 - 1) / (256 * 64));
   dim3 grid(4, ADMM_EST_CAND / 8, nz < 1 ? 1 : (nz > 32 ? 32 : nz));
+  KernelScope ks_("weight_est_kernel", st);
   weight_est_kernel<<<grid, 256, 0, st>>>(w, grad, per_gate, est_acc);
   count_launch();
   return check_launch("weight_est");
 }
 int launch_weight_select(const admm_problem& p, const double* est_acc, const double* fk_acc, const float* qmax,
                          const admm_probe_plan& plan, int final_pass, int32_t* done, float* theta, cudaStream_t st) {
+  KernelScope ks_("weight_select_kernel", st);
   weight_select_kernel<<<1, 32, 0, st>>>(est_acc, fk_acc, qmax, p.hp, p.T, plan, final_pass, done, theta);
   count_launch();
   return check_launch("weight_select");
@@ -467,6 +476,7 @@ int launch_weight_select(const admm_problem& p, const double* est_acc, const dou
 int launch_weight_apply(const admm_problem& p, int src, const float* grad, const float* theta, cudaStream_t st) {
   const int64_t per_gate = (int64_t)(src == ADMM_SRC_X ? p.D : p.H) * p.H;
   float* w = (src == ADMM_SRC_X) ? p.wx : p.wh;
+  KernelScope ks_("weight_apply_kernel", st);
   weight_apply_kernel<<<(unsigned)((4 * per_gate + 255) / 256), 256, 0, st>>>(w, grad, theta, p.hp, src, p.T, per_gate);
   count_launch();
   return check_launch("weight_apply");

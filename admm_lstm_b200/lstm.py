@@ -76,7 +76,11 @@ class LSTM(nn.Module):
     def forward(self, x: torch.Tensor, c: Optional[torch.Tensor] = None, h: Optional[torch.Tensor] = None):
         if self.with_grad:
             return self.grad_forward(x, c, h)
-        if x.is_cuda and c is None and h is None and not torch.is_grad_enabled():
+        # demo.py:341-342 evaluates `loss_func(model(train_x), train_y)` with autograd ENABLED on a model whose parameters an
+        # ADMM optimizer owns (requires_grad False): nothing can need a graph then, so the library's forward kernel runs
+        # (chunked over samples; no [N,T+1,H] temporaries).  Eager torch only when a gradient could actually flow.
+        if x.is_cuda and c is None and h is None and not (
+                torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
             from .optimizer import predict_cuda
             return predict_cuda(self, x)
         return self.init_gate_variables(x, c, h)["a"]

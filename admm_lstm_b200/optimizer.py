@@ -99,8 +99,8 @@ class ADMMBasedOptimizer(object):
                    'presharded' (each rank passes only its own samples).
       use_tensor_cores  None = automatic (tcgen05 path when the shape is eligible).
       probe        how the backtracking loop of the weight updates (admm.py:331-338) gets f(w + G/theta): 'moments'
-                   (default; one pass, every theta at once from a 4th-order expansion along the probe ray, valid because
-                   the perturbation of the pre-activations is < 2^-5 there -- checked on the device, exact passes follow if
+                   (default; one pass, every theta at once from a 6th-order expansion along the probe ray, valid where
+                   the perturbation of the pre-activations is <= 2^-4 -- checked on the device, exact passes follow if
                    not) or 'exact' (every candidate evaluated one by one).  Both replay the same comparison; they can
                    stop at different thetas only where the reference's own fp32 comparison is decided by rounding
                    (the "absorption exits" of SURVEY section 7), with no effect on the iterates at the parity tolerance.
@@ -122,6 +122,7 @@ class ADMMBasedOptimizer(object):
         self.variant, self.with_dual_y = variant, bool(with_dual_y)
         self.probe = probe or os.environ.get("ADMM_LSTM_PROBE", "moments")
         log_assert(self.probe in ("moments", "exact"), f"probe must be 'moments' or 'exact' (Got: {self.probe}).")
+        log_assert(sharding in ("slice", "presharded"), f"sharding must be 'slice' or 'presharded' (Got: {sharding}).")
         self.verbose = verbose
         self.summary = None
         self.comm = comm if comm is not None else Comm()
@@ -321,9 +322,18 @@ class ADMMBasedOptimizer(object):
             setattr(self.model, "h2" + g, nn.Parameter(self._wh[q], requires_grad=False))
         setattr(self.model, "out", nn.Parameter(self._wy, requires_grad=False))
         self._bound_ptrs = {name: getattr(self.model, name).data_ptr() for name in self._param_names()}
+        self._note_weight_versions()
+
+    def _note_weight_versions(self) -> None:
+        """torch's in-place version counters of the bound Parameters: the library's kernels write through raw pointers and
+        never bump them, every torch in-place write (load_state_dict's param.copy_, p.data.mul_(), ...) does."""
+        self._bound_versions = {name: getattr(self.model, name)._version for name in self._param_names()}
 
     def _resync_weights_if_replaced(self) -> None:
-        """If user code replaced a Parameter object (e.g. load_state_dict on a new module), import it."""
+        """Weights written behind the optimizer's back since the last step: a Parameter object replaced (set_weight,
+        blocks/lstm.py:35; load_state_dict on a new module) is imported; an in-place write into a bound Parameter
+        (model.load_state_dict(sd), p.data.mul_()) already changed the fp32 buffers, but the tensor-core operand copies
+        of the weights and the stored pre-activations are derived data and must be refreshed / dropped."""
         for name in self._param_names():
             if getattr(self.model, name).data_ptr() != self._bound_ptrs[name]:
                 self._pull_weights_from_model()
@@ -332,6 +342,11 @@ class ADMMBasedOptimizer(object):
                 if self._tc_ws is not None:
                     self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS, _stream_ptr())
                 return
+        if any(getattr(self.model, name)._version != self._bound_versions[name] for name in self._param_names()):
+            self._set_z_valid(False)
+            if self._tc_ws is not None:
+                self._call("admm_tc_refresh", self._pp, _lib.TC_WEIGHTS, _stream_ptr())
+            self._note_weight_versions()
 
     # ------------------------------------------------------------------------------------ plumbing
     def _call(self, name, *args) -> None:
@@ -445,7 +460,9 @@ class ADMMBasedOptimizer(object):
         if self._hint_q is not None:
             for g, q in enumerate(self._hint_q[src]):
                 if q == q and q > 2.0 ** -5:                      # NaN-safe
-                    k0[g] = min(_lib.ADMM_MAX_CAND, int(math.ceil(math.log2(q * 32.0)))) if math.isfinite(q) else _lib.ADMM_MAX_CAND
+                    if not math.isfinite(q) or q >= 2.0 ** (_lib.ADMM_MAX_CAND - 7):
+                        return full          # a diverging run: the expansion's window would not fit, go straight to the exact passes
+                    k0[g] = int(math.ceil(math.log2(q * 32.0)))    # <= ADMM_MAX_CAND - 2, so the proofs (k0 + 2) fit
         # proofs always cover two exponents more than the hint asks for (ncand = 2): max|Q| may grow by 8x between the
         # hint and this step before the exact passes are needed
         return [(tuple(k0), 2, 1, 1)] + full
@@ -599,7 +616,7 @@ class ADMMBasedOptimizer(object):
 
     def load_state(self, path: str) -> None:
         fn = f"{path}.rank{self.comm.rank}of{self.comm.world_size}.pt"
-        self.load_state_dict(torch.load(fn, map_location="cpu", weights_only=False))
+        self.load_state_dict(torch.load(fn, map_location="cpu", weights_only=True))   # tensors, str, numbers, tuples only
 
     # ------------------------------------------------------------------------------------ observables
     def metrics(self) -> Dict[str, float]:
@@ -620,6 +637,18 @@ class ADMMBasedOptimizer(object):
         self.last_metrics = out
         return out
 
+    def training_loss(self) -> float:
+        """MSE of the model on the WHOLE (global) training set -- what demo.py:341 computes every epoch with model(train_x) --
+        from the samples already resident in the device layout: no re-upload, no transposition, one scalar all-reduce when
+        the samples are sharded.  Synchronises."""
+        lib, dev = self._lib, self.device
+        out = torch.empty((self.output_size, self.ldn), dtype=torch.float32, device=dev)
+        _predict_feature_major(lib, dev, self._x, self.n_local, self._wx, self._wh, self._wy, out)
+        err = (out[:, : self.n_local] - self._y[:, : self.n_local]).double()
+        acc = torch.stack([(err * err).sum(), torch.tensor(float(err.numel()), dtype=torch.float64, device=dev)])
+        self.comm.allreduce_sum_(acc)
+        return float(acc[0] / acc[1])
+
     def theta_trace(self) -> Dict[str, float]:
         """theta chosen by the last step for each weight and for h_T (diagnostics; synchronises)."""
         th = self._theta_w.cpu()
@@ -628,26 +657,54 @@ class ADMMBasedOptimizer(object):
         return out
 
 
-def predict_cuda(model, x: torch.Tensor) -> torch.Tensor:
-    """model(x) for a CUDA batch through the library's forward kernel (reference: blocks/lstm.py:43-46,
-    evaluated by demo.py:341-342 on the train and validation sets every epoch)."""
-    lib = _lib.load()
-    dev = x.device
-    N, T, D = x.shape
-    H, O = model.hidden_size, model.output_size
-    ldn = _round_up(N, 128)
-    xt = _feature_major(x, ldn, dev)
-    wx = torch.stack([getattr(model, "x2" + g).detach() for g in _GATES]).contiguous().float()
-    wh = torch.stack([getattr(model, "h2" + g).detach() for g in _GATES]).contiguous().float()
-    wy = model.out.detach().contiguous().float()
+def _predict_feature_major(lib, dev, xt: torch.Tensor, n: int, wx, wh, wy, out: torch.Tensor) -> None:
+    """out [O][ldn] <- the model's prediction for the feature-major batch xt [T][D][ldn] (admm_predict)."""
+    T, D, ldn = xt.shape
+    H, O = wh.shape[1], wy.shape[1]
     work = torch.empty(4 * H * ldn, dtype=torch.float32, device=dev)
-    out = torch.empty((O, ldn), dtype=torch.float32, device=dev)
     p = _lib.Problem()
-    p.n, p.n_global, p.ldn = N, N, ldn
+    p.n, p.n_global, p.ldn = n, n, ldn
     p.T, p.D, p.H, p.O = T, D, H, O
     p.variant, p.with_dual_y = 0, 0
     p.x = xt.data_ptr()
     p.wx, p.wh, p.wy = wx.data_ptr(), wh.data_ptr(), wy.data_ptr()
     with torch.cuda.device(dev):
         _lib.check(lib.admm_predict(C.byref(p), work.data_ptr(), out.data_ptr(), _stream_ptr()), "admm_predict")
-    return out.t()[:N].contiguous()
+
+
+_PREDICT_CHUNK = 32768          # samples per admm_predict call: bounds the transposed copy of x and the 4*H*ldn work buffer
+
+
+def predict_cuda(model, x: torch.Tensor) -> torch.Tensor:
+    """model(x) for a CUDA batch through the library's forward kernel (reference: blocks/lstm.py:43-46,
+    evaluated by demo.py:341-342 on the train and validation sets every epoch).  Chunked over samples, so the only
+    temporaries are one chunk of x in the device layout and four [H, chunk] slabs -- the reference allocates six
+    [N, T+1, H] tensors per call."""
+    lib = _lib.load()
+    dev = x.device
+    N = x.shape[0]
+    O = model.output_size
+    wx = torch.stack([getattr(model, "x2" + g).detach() for g in _GATES]).contiguous().float()
+    wh = torch.stack([getattr(model, "h2" + g).detach() for g in _GATES]).contiguous().float()
+    wy = model.out.detach().contiguous().float()
+    result = torch.empty((N, O), dtype=torch.float32, device=dev)
+    for lo in range(0, N, _PREDICT_CHUNK):
+        n = min(_PREDICT_CHUNK, N - lo)
+        ldn = _round_up(n, 128)
+        xt = _feature_major(x[lo:lo + n], ldn, dev)
+        out = torch.empty((O, ldn), dtype=torch.float32, device=dev)
+        _predict_feature_major(lib, dev, xt, n, wx, wh, wy, out)
+        result[lo:lo + n] = out.t()[:n]
+    return result
+
+
+def sharded_mse_loss(model, x_local: torch.Tensor, y_local: torch.Tensor, comm: Optional[Comm] = None) -> float:
+    """nn.MSELoss()(model(x), y) (demo.py:316,341-342) over samples that are sharded across ranks: every rank
+    predicts its own samples with the library's forward kernel; ONE all-reduce of (sum of squared errors, element count)
+    gives the global mean on every rank."""
+    comm = comm if comm is not None else Comm()
+    pred = predict_cuda(model, x_local)
+    err = (pred - y_local.to(pred.device, torch.float32)).double()
+    acc = torch.stack([(err * err).sum(), torch.tensor(float(err.numel()), dtype=torch.float64, device=pred.device)])
+    comm.allreduce_sum_(acc)
+    return float(acc[0] / acc[1])

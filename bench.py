@@ -15,9 +15,11 @@ Workloads (synthetic data of the named shapes, random-init Xavier weights, Googl
   cfg4      configs[4] HAR-shaped classification T=128, D=9, H=512, O=6 at 32768 samples per GPU
   google    configs[0] shape N=4224, T=10, D=1, H=10
   small     a quick sanity shape
-`--impl reference` times the CPU restatement of the reference's own algorithm (oracle/, kind "port":
-the reference is Python and /root/reference does not travel to the GPU box) on the host cores, on a
-bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (its own admm.py / admm.no_dual_y.py / admm_l/main.py, staged byte
+for byte in oracle/_ref by oracle/make_ref.py and run by oracle/ref_runner.py in its own process, kind "reference") on the
+host cores, on a bounded sample of the same workload; if oracle/_ref is absent it falls back to the numpy restatement
+(oracle/admm_oracle.py, kind "port").  The B200 arm at one GPU also reports `gpu_baseline`: the same unmodified reference
+with device='cuda' (eager torch on the same B200) -- the reference's only existing GPU path.
 """
 from __future__ import annotations
 
@@ -82,6 +84,113 @@ def bench_params(pname, n_global, hidden):
     return {"rho": rho, "beta": dict(base["beta"])}
 
 
+# seconds of CPU work per sample and step() of the unmodified reference on ~16 host cores (measured: cfg3 0.19 s on 8 cores;
+# BASELINE.md section 2 for the H = 256 / 512 shapes, scaled by T), used only to SIZE the bounded sample
+REF_COST = {"cfg3": 0.12, "cfg2": 0.012, "cfg4": 0.05, "google": 0.35 / 4224, "small": 1e-4}
+REF_COST_L = {"cfg3": 0.35, "cfg2": 0.03, "cfg4": 0.12, "google": 0.6 / 4224, "small": 3e-4}
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def ref_sample_n(workload, variant, steps, warmup, budget_s):
+    """Bounded sample of the workload for the CPU arm: the whole (warmup + steps) run fits `budget_s` seconds."""
+    n_gpu = WORKLOADS[workload][0]
+    cost = (REF_COST_L if variant == "admm_l" else REF_COST)[workload]
+    n = int(budget_s / max(steps + warmup, 1) / cost)
+    if workload == "google":
+        return n_gpu                                   # the reference's own CPU-runnable case: always at full size
+    # below ~32 samples the reference's step time stops shrinking (its [N,H]x[H,H] products become weight-bandwidth bound:
+    # cfg3 6.3 s/step at N = 16, 6.1 s at N = 32, 26.5 s at N = 128 on 8 cores), which would understate its throughput
+    return max(32, min(n_gpu, n // 8 * 8))
+
+
+def run_reference(workload, variant, n, steps, warmup, device, threads=None, timeout=1500):
+    """Time the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) through oracle/ref_runner.py in its own
+    process.  device 'cpu' hides the GPUs from that process (the reference picks CUDA whenever it sees one,
+    _global.py:217).  Returns (info dict, mean seconds per step) or (None, reason)."""
+    import numpy as np
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "admm.py")):
+        return None, "oracle/_ref not staged"
+    n_gpu, t, d, h, o, pname, cpu_n, cls = WORKLOADS[workload]
+    threads = threads or host_threads()
+    with tempfile.TemporaryDirectory(prefix="admm_ref_") as tmp:
+        path = os.path.join(tmp, "problem.npz")
+        if variant == "admm_l":
+            x, y, _ = make_data(n, t, d, h, 1, 0, False)
+            np.savez(path, x=x, y=y, params_json=json.dumps({}), **make_l_weights(d, h))
+        else:
+            x, y, w = make_data(n, t, d, h, o, 0, cls)
+            np.savez(path, x=x, y=y, params_json=json.dumps(bench_params(pname, n, h)), **w)
+        env = dict(os.environ)
+        if device == "cpu":
+            env["CUDA_VISIBLE_DEVICES"] = ""
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--data", path, "--variant", variant,
+               "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads)]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=tmp)
+        except subprocess.TimeoutExpired:
+            return None, f"reference run exceeded {timeout} s"
+    if r.returncode != 0:
+        return None, "reference run failed: " + (r.stderr.strip().splitlines() or ["?"])[-1][:300]
+    try:
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    except (ValueError, IndexError):
+        return None, "reference run printed no JSON"
+    if "unavailable" in out or not out.get("step_s"):
+        return None, out.get("unavailable", "no timed steps")
+    dt = sum(out["step_s"]) / len(out["step_s"])
+    out["dt"] = dt
+    return out, dt
+
+
+def time_reference_cpu(workload, variant, steps, warmup, budget_s=150.0):
+    """CPU arm: the unmodified reference on all host cores (kind "reference"); numpy port (kind "port") only if oracle/_ref
+    is not staged."""
+    t = WORKLOADS[workload][1]
+    n = ref_sample_n(workload, variant, steps, warmup, budget_s)
+    threads = host_threads()
+    out, dt = run_reference(workload, variant, n, steps, warmup, "cpu", threads)
+    if out is None:
+        base, dt2 = (time_oracle_l(workload, steps, warmup) if variant == "admm_l" else time_oracle(workload, steps, warmup))
+        base["sample"] += f" [unmodified reference unavailable: {dt}]"
+        return base, dt2
+    fname = {"admm": "admm.py", "no_dual_y": "admm.no_dual_y.py", "admm_l": "comparison_experiment/admm_l/main.py"}[variant]
+    return {"value": n * t / dt, "unit": "sample-timestep updates/s", "cores": out["threads"], "kind": "reference",
+            "sample": f"UNMODIFIED reference {fname} (oracle/_ref, torch {out['torch']} CPU, {out['threads']} threads), same "
+                      f"T/D/H/O, N={n} samples, {steps} step(s) after {warmup} warm-up, {dt:.2f} s/step"}, dt
+
+
+def time_reference_gpu(workload, variant, n, steps=2, warmup=1):
+    """The unmodified reference with device='cuda' (eager torch / cuBLAS) on this box's GPU 0: SURVEY 2a's "existing GPU
+    path" bar.  Runs in its own process BEFORE the B200 arm allocates its state."""
+    t = WORKLOADS[workload][1]
+    out, dt = run_reference(workload, variant, n, steps, warmup, "cuda", timeout=900)
+    if out is None:
+        return {"unavailable": dt}
+    if not str(out.get("device", "")).startswith("cuda"):
+        return {"unavailable": f"reference ran on {out.get('device')}"}
+    return {"value": n * t / dt, "unit": "sample-timestep updates/s", "kind": "reference", "ms_per_step": dt * 1e3,
+            "sample": f"UNMODIFIED reference (oracle/_ref) with device='cuda' (eager torch {out['torch']}) on {out.get('gpu')}, "
+                      f"same T/D/H/O, N={n} samples ({out.get('peak_mem_gb', 0):.1f} GB peak), {steps} step(s) after {warmup} "
+                      f"warm-up, {dt:.2f} s/step"}
+
+
+def blas_threads():
+    """Threads numpy's BLAS actually uses (torchrun exports OMP_NUM_THREADS=1: report what ran, not the core count)."""
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(i.get("num_threads", 1)) for i in threadpool_info()] or [1])
+    except Exception:
+        return 1
+
+
 def time_oracle(workload, steps, warmup, threads=None):
     """CPU arm: oracle/admm_oracle.py (numpy + multithreaded BLAS) on a bounded sample."""
     import numpy as np  # noqa: F401
@@ -99,7 +208,7 @@ def time_oracle(workload, steps, warmup, threads=None):
     for _ in range(steps):
         ora.step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    cores = threads or os.cpu_count() or 1
+    cores = blas_threads()
     return {"value": cpu_n * t / dt, "unit": "sample-timestep updates/s", "cores": cores, "kind": "port",
             "sample": f"oracle/admm_oracle.py (numpy fp32 + OpenBLAS, {cores} threads), same T/D/H/O, N={cpu_n} samples, "
                       f"{steps} step(s) after {warmup} warm-up, {dt:.2f} s/step"}, dt
@@ -129,7 +238,7 @@ def time_oracle_l(workload, steps, warmup):
     for _ in range(steps):
         ora.step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    cores = os.cpu_count() or 1
+    cores = blas_threads()
     return {"value": cpu_n * t / dt, "unit": "sample-timestep updates/s", "cores": cores, "kind": "port",
             "sample": f"oracle/admm_l_oracle.py (numpy fp32 + OpenBLAS, {cores} threads), same T/D/H, N={cpu_n} samples, "
                       f"{steps} step(s) after {warmup} warm-up, {dt:.2f} s/step"}, dt
@@ -237,7 +346,7 @@ def bench_admm_l(args, rank, world, local_rank, config, metric, unit):
                 "kernel_ms_per_step": {k: round(v[1] / 2, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},
                 "thetas": {k: float(v) for k, v in opt.thetas.items()}}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = time_oracle_l(args.workload, 1, 0)
+            line["cpu_baseline"], _ = time_reference_cpu(args.workload, "admm_l", 1, 1, budget_s=24.0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -291,6 +400,81 @@ class ClockSampler:
         return out
 
 
+def kernel_report(lib):
+    """{kernel class: (launches, total ms)} from the library's own event records (admm_kernel_timing_report)."""
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.admm_kernel_timing_report(buf, len(buf))
+    out = {}
+    if n <= 0:
+        return out
+    for ln in buf.value.decode().splitlines():
+        name, calls, ms = ln.split("\t")
+        out[name] = (int(calls), float(ms))
+    return out
+
+
+def kernel_table(kern, ksteps, opt, T, D, H, peaks, ms_step):
+    """Per-kernel roofline rows of one step (main variants): algorithmic bytes / useful flops per sample-timestep (DESIGN.md
+    section 4: what the kernel must move / compute, fp32 state, fp16-pair side buffers counted where they are the
+    operand), the bound they imply, and the achieved fraction of the MEASURED peak.  `dram_bytes` = ncu
+    dram__bytes_read+write per step from profiles/ncu_traffic.json when a capture of this shape is committed."""
+    st_ = float(opt.n_local) * T                      # sample-timesteps per step on this GPU
+    z = 4.0 if opt.keeps_preactivations else 0.0
+    # name -> (bytes per s-t, useful flops per s-t, what it is)
+    model = {
+        "gate_gemm_tc<SWEEP>": ((22 + z) * H * 4 + D * 4, 8.0 * H * (D + H), "sweep: gate GEMM + i,f,g,o,c,h + duals (a5-a10)"),
+        "gate_gemm_simt_kernel": ((22 + z) * H * 4 + D * 4, 8.0 * H * (D + H), "CUDA-core gate GEMM (all modes)"),
+        "grad_from_z_kernel": (20.0 * H * 4, 0.0, "x-phase residual R from stored z (reads z,lambda,gate; writes R hi/lo)"),
+        "atr_tc<64,tf32>": (8.0 * H * 4 + 2 * D * 4, 8.0 * H * D, "x-phase G = x^T R (3xTF32)"),
+        "atr_tc<128,tf32>": (8.0 * H * 4 + 2 * D * 4, 8.0 * H * D, "x-phase G = x^T R (3xTF32)"),
+        "atr_tc<256,tf32>": (8.0 * H * 4 + 2 * D * 4, 8.0 * H * D, "x-phase G = x^T R (3xTF32)"),
+        "gate_gemm_tc<RAWZ:Q=x*G>": (4.0 * H * 4 + D * 4, 8.0 * H * D, "x-phase probe operand Q = x G"),
+        "gate_gemm_tc<RAWZ:Q=h*G>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase probe operand Q = h G"),
+        "gate_gemm_tc<RAWZ:z>": (4.0 * H * 4 + (D + H) * 4, 8.0 * H * (D + H), "pre-activations (no z store)"),
+        "probe_moments_kernel": (2 * 16.0 * H * 4, 0.0, "moment pass of both phases (reads z0,Q,lambda,gate)"),
+        "probe_eval_kernel": (0.0, 0.0, "exact / lower-bound candidate passes (subset of the units)"),
+        "gate_gemm_tc<GRAD:z+=x*dW>": (20.0 * H * 4 + D * 4, 8.0 * H * D, "h-phase: z += x dW, residual R as fp16 pair"),
+        "gate_gemm_tc<GRAD:full>": (12.0 * H * 4 + (D + H) * 4, 8.0 * H * (D + H), "gradient pass with its own GEMM (no valid z store)"),
+        "atr_tc<256,f16>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase G = h^T R (fp16 pairs)"),
+        "atr_tc<128,f16>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase G = h^T R (fp16 pairs)"),
+        "atr_tc<64,f16>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase G = h^T R (fp16 pairs)"),
+    }
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        for ent in json.load(open(tpath)).get("kernels", []):
+            if (ent.get("n_local"), ent.get("H"), ent.get("D"), ent.get("T")) == (opt.n_local, H, D, T):
+                traffic[ent["kernel"]] = ent
+    tc_ceiling = peaks["bf16_tflops_sustained"] / 3.0
+    ridge = tc_ceiling * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    rows, other_ms = [], 0.0
+    for name, (calls, ms) in sorted(kern.items(), key=lambda kv: -kv[1][1]):
+        ms_s = ms / ksteps
+        if name not in model or ms_s < 0.002 * ms_step:
+            other_ms += ms_s
+            continue
+        b, f, what = model[name]
+        row = {"kernel": name, "what": what, "launches_per_step": calls // ksteps, "ms_per_step": round(ms_s, 3),
+               "share_of_step": round(ms_s / ms_step, 4)}
+        if b > 0 or f > 0:
+            gbs = b * st_ / (ms_s * 1e-3) / 1e9
+            tfs = f * st_ / (ms_s * 1e-3) / 1e12
+            bound = "tensor" if (b > 0 and f / b > ridge) else "hbm"
+            row.update({"bound": bound, "algorithmic_bytes_per_step": b * st_, "useful_flops_per_step": f * st_,
+                        "achieved_gbs": round(gbs, 1), "achieved_tflops": round(tfs, 1),
+                        "frac": round(tfs / peaks["bf16_tflops_sustained"] if bound == "tensor" else gbs / peaks["hbm_gbs"], 4)})
+            if bound == "tensor":
+                row["frac_of_3xfp16_ceiling"] = round(tfs / tc_ceiling, 4)
+            if name in traffic:
+                row["dram_bytes_per_step"] = traffic[name]["dram_bytes_per_step"]
+                row["dram_source"] = traffic[name]["source"]
+        rows.append(row)
+    rows.append({"kernel": "other (prep, select/apply, Wy, t = T tail)", "ms_per_step": round(other_ms, 3),
+                 "share_of_step": round(other_ms / ms_step, 4)})
+    return rows
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -311,6 +495,10 @@ def main():
                     help="admm / no_dual_y: the reference's admm.py / admm.no_dual_y.py; admm_l: ADMM-LSTM-L (admm_l/main.py)")
     ap.add_argument("--n-per-gpu", type=int, default=0, help="override the per-GPU sample count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-torch device='cuda' run of the unmodified reference")
+    ap.add_argument("--gpu-baseline-n", type=int, default=0, help="samples of the eager-GPU reference run (default: per workload)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="CPU seconds the whole --impl reference run may take")
+    ap.add_argument("--strong", type=int, default=0, help="strong scaling: TOTAL sample count, split over the ranks")
     ap.add_argument("--no-tc", action="store_true", help="force the fp32 CUDA-core path")
     ap.add_argument("--kernel-timing", default="separate", choices=["separate", "inline", "off"],
                     help="per-entry-point CUDA-event timing: in separate extra steps (default), inside the timed steps, or off")
@@ -322,23 +510,25 @@ def main():
     n_gpu, T, D, H, O, pname, cpu_n, cls = WORKLOADS[args.workload]
     if args.n_per_gpu:
         n_gpu = args.n_per_gpu
+    scaling = "weak"
+    if args.strong:
+        n_gpu, scaling = args.strong // max(world, 1), "strong"
     metric = "ADMM sample-timestep updates/sec"
     unit = "sample-timestep updates/s"
     config = {"workload": WORKLOAD_DESC[args.workload], "name": args.workload, "variant": args.variant,
               "samples_per_gpu": n_gpu, "T": T, "D": D, "H": H, "O": O, "hyper_parameters": pname + " as shipped, rho_y rescaled to keep rho_y*N*H at the GoogleStock value (bench_params)",
-              "parallelism": f"sample-sharded dp{max(world, 1)}",
+              "parallelism": f"sample-sharded dp{max(world, 1)}", "scaling_mode": scaling,
               "l2": "state per GPU is far larger than the 126 MB L2; no explicit flush"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        if args.variant == "admm_l":
-            base, dt = time_oracle_l(args.workload, max(args.steps, 1), min(args.warmup, 1))
-        else:
-            base, dt = time_oracle(args.workload, max(args.steps, 1), min(args.warmup, 1))
+        # exactly --warmup untimed and --steps timed steps of the unmodified reference; the sample is sized so that the
+        # whole run stays within a few minutes
+        base, dt = time_reference_cpu(args.workload, args.variant, max(args.steps, 1), max(args.warmup, 0), args.ref_budget_s)
         line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus,
-                "steps": max(args.steps, 1), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+                "steps": max(args.steps, 1), "warmup": max(args.warmup, 0), "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -354,6 +544,13 @@ def main():
     from admm_lstm_b200.lstm import LSTM
     from admm_lstm_b200.optimizer import ADMMBasedOptimizer
     from admm_lstm_b200.parameters import example_parameter_dictionary as epd
+
+    gpu_baseline = None
+    if world == 1 and not args.no_gpu_baseline:
+        # the unmodified reference with device='cuda' (eager torch) on this GPU, in its own process, before this arm
+        # allocates its state (N = 4096 for the synthetic shapes, the full set for GoogleStock)
+        gb_n = args.gpu_baseline_n or {"cfg3": 4096, "cfg2": 16384, "cfg4": 4096, "google": 4224, "small": 4096}[args.workload]
+        gpu_baseline = time_reference_gpu(args.workload, args.variant, min(gb_n, n_gpu))
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -420,6 +617,15 @@ def main():
         barrier()
     ksum = opt.kernel_time_summary() if args.kernel_timing != "off" else {}
     opt.enable_kernel_timing(False)
+    # per-KERNEL timing (CUDA events recorded by the library around every launch, admm_kernel_timing) in two more steps
+    kern = {}
+    if args.kernel_timing != "off":
+        lib.admm_kernel_timing(1)
+        for _ in range(2):
+            opt.step()
+        barrier()
+        kern = kernel_report(lib)
+        lib.admm_kernel_timing(0)
 
     # ---- timed region 2: end to end through the public API with host buffers --------------------------
     pinned = {"wx": torch.empty((4, D, H)).pin_memory(), "wh": torch.empty((4, H, H)).pin_memory(),
@@ -485,14 +691,15 @@ def main():
                     if (ent["n_local"], ent["H"], ent["D"]) == (opt.n_local, H, D) and opt.uses_tensor_cores:
                         roofline["traffic"] = ent["dram_bytes_per_launch"]
                         roofline["traffic_source"] = ent["source"]
+        kernels = kernel_table(kern, 2, opt, T, D, H, peaks, ms_step)
         step_flops = 56.0 * H * (D + H) * opt.n_local * T
         line = {
             "metric": metric, "value": n_total * T / (ms_step * 1e-3), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": n_total * T / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "tensor_cores": bool(opt.uses_tensor_cores),
             "step_tflops_useful": step_flops / (ms_step * 1e-3) / 1e12,
             "kernel_ms_per_step": {k: round(v[1] / ksteps, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},
@@ -501,8 +708,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             # one warm-up step first: the first iteration from the forward-initialised state leaves the backtracking
             # loops early and runs ~4x faster than every later one; the GPU value above is a steady-state step too
-            base, _ = time_oracle(args.workload, 1, 1)
+            base, _ = time_reference_cpu(args.workload, args.variant, 1, 1, budget_s=24.0)
             line["cpu_baseline"] = base
+        if gpu_baseline is not None:
+            line["gpu_baseline"] = gpu_baseline
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -215,6 +215,14 @@ int admm_debug_preact(const admm_problem* p, int t, float* out, int use_tc, void
  * (bench.py reports it as gpu_launches). */
 int64_t admm_launch_count(int reset);
 
+/* Per-kernel timing (measurement only; the reference has wall-clock timing of step() alone, demo.py:73-120,354-356).
+ * admm_kernel_timing(1) makes every kernel launch of this library record a CUDA-event pair on its stream (returns the
+ * previous setting; enabling drops earlier records); admm_kernel_timing_report() synchronises on the recorded events and
+ * writes one line per kernel class, "name<TAB>launches<TAB>total_ms<LF>", NUL-terminated, into the HOST buffer buf[len],
+ * clearing the records; returns the number of bytes written or a negative ADMM_E* code. */
+int admm_kernel_timing(int enable);
+int64_t admm_kernel_timing_report(char* host_buf, int64_t len);
+
 /* ================================================================================================================
  * ADMM-LSTM-L: the linearised ADMM of
  * /root/reference/comparison_experiment/admm_l/admm_lstm.py driven by admm_l/main.py:139-191.

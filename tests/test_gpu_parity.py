@@ -570,3 +570,68 @@ def test_large_probe_steps_take_the_exact_passes(shape, tc):
     for k in WKEYS:
         if k != "out":
             assert rel_err(wg[k], ora.w[k]) < 5e-4, (k, rel_err(wg[k], ora.w[k]))
+
+
+def test_inplace_weight_write_is_noticed():
+    """model.load_state_dict(sd) / p.data.mul_() write INTO the bound Parameters (same data_ptr): the fp16-pair
+    weight operands and the stored pre-activations of the tensor-core path are derived data and must follow.  Reference
+    behaviour: set_weight / setattr simply replace the tensor (blocks/lstm.py:31-41), no hazard there."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    n, t, d, h, o = 300, 4, 16, 64, 1
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=23)
+    ma, a = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    mb, b = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    assert a.keeps_preactivations
+    a.step()
+    b.step()
+    sd = {k: v.detach().clone() * 0.9 for k, v in ma.state_dict().items()}
+    ma.load_state_dict(sd)                       # nn.Module.load_state_dict -> param.copy_(): in place, data_ptr unchanged
+    with torch.no_grad():
+        for k, v in mb.state_dict().items():
+            v.mul_(0.9)
+    b.state_changed()                            # the explicit route (tests use it after writing buffers directly)
+    for _ in range(2):
+        a.step()
+        b.step()
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert np.array_equal(wa[k], wb[k]), k
+    # and against the oracle restarted from the same modified weights and state is covered by b's route (test_*_vs_oracle)
+
+
+def test_forward_takes_the_library_kernel_with_grad_enabled():
+    """SURVEY 8 f2 on the path the reference actually calls: demo.py:341-342 evaluates model(train_x) with autograd ENABLED.
+    With the parameters owned by an ADMM optimizer (requires_grad False) that call must run admm_predict, not eager torch."""
+    _need_gpu()
+    from gpu_utils import make_opt
+    from admm_lstm_b200 import _lib
+    from admm_lstm_b200.optimizer import sharded_mse_loss
+    n, t, d, h, o = 700, 6, 5, 24, 2
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=31)
+    model, opt = make_opt(w, x, y, GOOGLE, "admm")
+    opt.step()
+    xc, yc = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    lib = _lib.load()
+    assert torch.is_grad_enabled()
+    before = lib.admm_launch_count(0)
+    pred = model(xc)                                             # grad enabled, as demo.py calls it
+    assert lib.admm_launch_count(0) - before >= t, "model(x) did not go through the library's forward kernel"
+    ref = model.init_gate_variables(xc)["a"]                     # eager torch (blocks/lstm.py:65-88)
+    np.testing.assert_allclose(pred.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    loss = float(torch.nn.functional.mse_loss(pred, yc))
+    assert abs(opt.training_loss() - loss) < 1e-5 * loss         # resident-data evaluation, same number
+    assert abs(sharded_mse_loss(model, xc, yc) - loss) < 1e-5 * loss
+    # chunked over samples: results independent of the chunk size
+    import admm_lstm_b200.optimizer as om
+    old = om._PREDICT_CHUNK
+    try:
+        om._PREDICT_CHUNK = 256
+        np.testing.assert_array_equal(model(xc).cpu().numpy(), pred.cpu().numpy())
+    finally:
+        om._PREDICT_CHUNK = old
+    # a model whose parameters DO require grad keeps the differentiable eager path
+    from admm_lstm_b200.lstm import LSTM
+    m2 = LSTM(d, h, o).cuda()
+    out = m2(xc)
+    assert out.requires_grad

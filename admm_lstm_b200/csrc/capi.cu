@@ -180,6 +180,8 @@ int admm_forward_t(const admm_problem* p, int t, void* stream) {
   if (p->tc_ws && tc_eligible(p) && p->zstore) { a.zstore = p->zstore; a.zT = p->T; a.zt0 = t - 1; }
   rc = run_gate_gemm(GG_FORWARD, p, a, 1, st);
   if (rc) return rc;
+  // the forward pass is the initialisation (admm.py:164-173: duals are zero, gates are activations): |R| <= 2
+  if (t == p->T && p->tc_ws && tc_eligible(p) && (rc = tc_set_bound(p, 2.0f, st))) return rc;
   if (t == p->T && p->a)
     return launch_output(p->gate[5] + (int64_t)p->T * p->H * p->ldn, p->wy, p->a, p->ldn, p->H, p->O, st);
   return ADMM_OK;
@@ -231,9 +233,11 @@ int admm_weight_begin(const admm_problem* p, int src, void* stream) {
   ADMM_REQUIRE(src == ADMM_SRC_X || src == ADMM_SRC_H, "admm_weight_begin: bad src");
   const bool use_tc = p->tc_ws && tc_eligible(p);
   if (src == ADMM_SRC_X && use_tc) {
-    // the x-phase gradient pass measures the bound on |R| that scales the h-phase's fp16 A^T R operand
-    if (cudaMemsetAsync(tc_r_bound(p), 0, sizeof(unsigned), (cudaStream_t)stream) != cudaSuccess)
-      return check_launch("r_bound memset");
+    // the bound on |R| that scales the fp16 operand of both A^T R GEMMs: measured by the previous sweep over the lambda / gate
+    // values it wrote (or by the forward initialisation / admm_tc_refresh(ADMM_TC_STATE)); they do not change in the weight phase
+    if (cudaMemcpyAsync(tc_r_bound(p), tc_x_bound(p), sizeof(unsigned), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) !=
+        cudaSuccess)
+      return check_launch("r_bound copy");
   }
   if (src == ADMM_SRC_H && p->zstore && p->wx_prev && use_tc) return tc_refresh_wx_delta(p, (cudaStream_t)stream);
   return ADMM_OK;
@@ -252,10 +256,10 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
   const bool atr_on_tc = use_tc;
   a.scratch = scratch; a.tc = tc; a.fw_acc = fw_acc; a.src = src;
   a.scratch_q = atr_on_tc ? scratch + 4LL * p->H * tc * p->ldn : nullptr;     // tf32 low part of R^T
-  // tensor-core path: the x-phase (K = D, cheap) keeps 3xTF32 and measures max(1 + |lambda/rho| + |gate|) >= |R|; the
-  // h-phase (K = H) writes R^T as fp16 pairs scaled from that bound and runs the fp16 A^T R GEMM
-  const bool r16 = use_tc && src == ADMM_SRC_H;
-  if (use_tc && src == ADMM_SRC_X) a.bound_track = tc_r_bound(p);
+  // tensor-core path: R^T is written as fp16 pairs scaled from the bound 1 + max(|lambda/rho| + |gate|) >= |R| (known before
+  // the phase starts, admm_weight_begin) and the fp16 A^T R GEMM runs; an x-phase with fewer than 8 input features keeps
+  // fp32 R for the CUDA-core reduction
+  const bool r16 = use_tc && (src == ADMM_SRC_H || p->D >= 8);
   if (r16) {
     a.r_bound = tc_r_bound(p);
     a.r16_hi = reinterpret_cast<__half*>(scratch);
@@ -273,7 +277,8 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
     e.n = p->n; e.ldn = p->ldn; e.H = p->H; e.tc = tc; e.zT = p->T; e.zt0 = t0; e.zstore = p->zstore;
     for (int g = 0; g < 4; ++g) { e.gate[g] = a.gate[g]; e.dual[g] = a.dual[g]; e.rho[g] = p->hp.rho[g]; }
     e.s_tstride = a.s_tstride;
-    e.r = a.scratch; e.r_lo = a.scratch_q; e.fw_acc = fw_acc; e.bound_track = a.bound_track;
+    e.r = a.scratch; e.r_lo = a.scratch_q; e.fw_acc = fw_acc; e.bound_track = nullptr;
+    e.r16_hi = a.r16_hi; e.r16_lo = a.r16_lo; e.r_bound = a.r_bound;
     rc = grad_from_z(e, st);
   } else {
     rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
@@ -333,6 +338,24 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
   a.scratch = scratch; a.scratch_q = scratch + half;
   const bool stored = p->tc_ws && tc_eligible(p) && p->zstore && p->wx_prev;
   if (stored) { a.zstore = p->zstore; a.zT = p->T; a.zt0 = t0; }
+  if (stored && plan->moments) {
+    // fused moment pass: Q = A_src G stays in TMEM, the GEMM's epilogue accumulates the moment sums and (on one unit per
+    // tile) the lower-bound proofs below the expansion -- no Q round trip through HBM, no separate proof passes
+    static const int fused = [] {
+      const char* e = getenv("ADMM_FUSED_MOMENTS");      // A/B switch for measurements
+      return e ? atoi(e) : 1;
+    }();
+    bool ok = fused != 0;
+    for (int g = 0; g < 4; ++g) {
+      a.mom_k0[g] = plan->k0[g];
+      a.mom_pc[g] = plan->proof ? plan->k0[g] + plan->ncand : 0;
+      ok = ok && a.mom_pc[g] <= 8 && plan->k0[g] < 64;
+    }
+    if (ok) {
+      a.fk_acc = fk_acc; a.qmax = qmax;
+      return run_gate_gemm(GG_MOMENTS, p, a, tc, st);
+    }
+  }
   rc = run_gate_gemm(GG_PROBE, p, a, tc, st);
   if (rc) return rc;
   ProbeEvalArgs e;
@@ -403,7 +426,18 @@ int admm_sweep_t(const admm_problem* p, int t, double* metrics, void* stream) {
   a.metrics = metrics;
   // keep z_t: it is the pre-activation the next iteration's x-phase gradient starts from (admm_problem::z_valid)
   if (p->tc_ws && tc_eligible(p) && p->zstore) { a.zstore = p->zstore; a.zT = p->T; a.zt0 = t - 1; }
-  return run_gate_gemm(GG_SWEEP, p, a, 1, (cudaStream_t)stream);
+  const bool use_tc = p->tc_ws && tc_eligible(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc) {
+    // the sweep measures the bound on |R| of the next iteration's gradient passes while it writes lambda and the gates
+    a.xbound_track = tc_x_bound(p);
+    if (t == 1 && cudaMemsetAsync(a.xbound_track + 1, 0, sizeof(unsigned), st) != cudaSuccess) return check_launch("x_bound memset");
+  }
+  rc = run_gate_gemm(GG_SWEEP, p, a, 1, st);
+  if (rc || !use_tc || t != p->T) return rc;
+  if (cudaMemcpyAsync(a.xbound_track, a.xbound_track + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return check_launch("x_bound publish");
+  return ADMM_OK;
 }
 
 int admm_last_probe(const admm_problem* p, double* sums, void* stream) {
@@ -435,6 +469,7 @@ int admm_tc_refresh(const admm_problem* p, int what, void* stream) {
   if ((what & ADMM_TC_INPUTS) && (rc = tc_refresh_inputs(p, st))) return rc;
   if ((what & ADMM_TC_WEIGHTS) && !(what & ADMM_TC_INPUTS) && (rc = tc_refresh_weights(p, st))) return rc;
   if ((what & ADMM_TC_STATE) && (rc = tc_refresh_state(p, st))) return rc;
+  if ((what & ADMM_TC_STATE) && (rc = tc_refresh_bound(p, st))) return rc;
   return ADMM_OK;
 }
 

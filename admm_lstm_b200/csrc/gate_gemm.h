@@ -8,7 +8,8 @@
 
 namespace admm {
 
-enum GateGemmMode { GG_FORWARD = 0, GG_SWEEP = 1, GG_GRAD = 2, GG_PROBE = 3, GG_RAWZ = 7 /* Z -> scratch */ };
+enum GateGemmMode { GG_FORWARD = 0, GG_SWEEP = 1, GG_GRAD = 2, GG_PROBE = 3, GG_MOMENTS = 4 /* Q + moment sums, fused */,
+                    GG_RAWZ = 7 /* Z -> scratch */ };
 
 // All pointers are pre-offset to the first timestep of the launch (grid.z index tl = 0);
 // x_tstride / s_tstride are the element strides from one timestep slab to the next.
@@ -48,6 +49,18 @@ struct GateGemmArgs {
   __half* r16_hi;
   __half* r16_lo;
   int32_t epi_prefetch;  // tensor-core path, SWEEP: L2 prefetch of the epilogue's next batch of units (set by gate_gemm_tc)
+  // SWEEP on the tensor-core path: receives max (1 + |lambda_g/rho_g| + |gate_g|) over the values the sweep WRITES, g = i,f,g,o
+  // (bit pattern, atomicMax).  Those are exactly what the next iteration's gradient passes read, so the bound on |R| that
+  // scales the fp16 operand of A^T R is known before the x-phase starts and its R^T can be fp16 pairs too.
+  unsigned* xbound_track;
+  // MOMENTS (tensor-core path with a valid z store): the probe operand Q = A_src G stays in TMEM and the epilogue accumulates
+  // the moment sums of admm_probe_plan::moments straight from it (Q never goes to HBM): fk_acc[g][ADMM_FK_MOMENTS + 0..6],
+  // qmax[g], and -- on ONE unit per 64-unit tile, a rigorous lower bound like the 1/8 subsets of the unfused path -- the exact
+  // sums of the candidates k < mom_pc[g] into fk_acc[g][ADMM_MAX_CAND + 1 + k].  mom_k0 = the plan's k0 (normalisation of Q).
+  int32_t mom_k0[4];
+  int32_t mom_pc[4];     // proof candidates per gate, <= 8
+  double* fk_acc;
+  float* qmax;
 };
 
 int gate_gemm_simt(int mode, const GateGemmArgs& a, int tc, cudaStream_t st);
@@ -113,6 +126,11 @@ struct GradFromZArgs {
   float* r_lo;
   double* fw_acc;         // [4]
   unsigned* bound_track;  // max (1 + |lambda/rho| + |gate|) over the elements read (bit pattern, atomicMax) or nullptr
+  // fp16-pair output (when the bound on |R| is already known, GateGemmArgs::xbound_track): R 2^sR as hi / lo halves in the
+  // layout of r / r_lo (half the bytes), sR = cap(*r_bound); nullptr -> fp32 R and its tf32 low part
+  __half* r16_hi;
+  __half* r16_lo;
+  const unsigned* r_bound;
 };
 int grad_from_z(const GradFromZArgs& a, cudaStream_t st);
 

@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <map>
 #include <mutex>
@@ -44,6 +45,14 @@ struct TcMaps {
   CUtensorMap x, x_lo, h, h_lo;         // fp16 hi / lo halves of x 2^sX and h 2^SCALE_H; dims (ldn, K, slabs)
   CUtensorMap wx_hi, wx_lo, wh_hi, wh_lo;   // dims (H, K, 4)
   CUtensorMap gx_hi, gx_lo;             // gradient of the probed weight, dims (H, Ksrc, 4)
+};
+
+// fp32 tensor maps of the state streams of the staged epilogue: a state tensor [T+1][H][ldn] viewed as
+// (sample, unit-in-group 16, unit group H/16, slab) with box (128, 1, 4, 1): ONE TMA instruction fetches, for one
+// unit-step, the 128-sample rows of the four unit groups the sixteen epilogue warps work on (4 x 512 B, dense in shared
+// memory as [group][sample]).  zstore [4][H][zT][ldn] is 5-D, its box takes all four gates at once.
+struct StateMaps {
+  CUtensorMap gate[6], dual[5], dual_h, zstore;
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -75,6 +84,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, 
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
@@ -317,6 +335,10 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
                 __stcs(p.zstore + g * zgate + zoff[e], z[g][eb + e]);
             }
             if (ok) { msum[0] += r.prim_sq; msum[1] += r.dual_sq; msum[2] += r.penalty; }
+            if (p.xbound_track)
+              msum[4] = fmaxf(fmaxf(fmaxf(msum[4], fmaf(fabsf(r.li), inv_rho_g[0], fabsf(r.i))),
+                                    fmaxf(fmaf(fabsf(r.lf), inv_rho_g[1], fabsf(r.f)), fmaf(fabsf(r.lg), inv_rho_g[2], fabsf(r.g)))),
+                              fmaf(fabsf(r.lo), inv_rho_g[3], fabsf(r.o)));
           }
         }
         if (MODE == GG_GRAD) {
@@ -369,25 +391,273 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Staged epilogue inputs (SWEEP and the h-phase GRAD refresh).  In the epilogue above every state value is a global load
+// issued from the epilogue warps' own registers: with 16 warps per SM the loads in flight are bounded by the register
+// file, the warps sit in long_scoreboard stalls (round 1: issue 46 %, DRAM 40 %) and an L2 prefetch was the only lever.
+// Here a dedicated LOADER warp streams the state rows of the tile into a shared-memory ring with TMA box copies
+// (cp.async.bulk.tensor ... mbarrier::complete_tx), up to S_STAGES unit-steps ahead of the epilogue and independent of it, so the
+// memory pipeline stays full while the epilogue warps only read shared memory (~30 cycles), compute and store.
+//   stage = one unit per unit group (4 groups of 16 units: what the 16 epilogue warps consume at the same time)
+//           x 128 samples x S_STREAMS state streams; one TMA box (StateMaps) per stream and stage; 16 stages per tile.
+// (A first version issued the 48 rows of a stage as 1-D bulk copies with per-lane addresses: ptxas serialises those
+// through the uniform datapath -- ELECT / R2UR / UBLKCP per lane -- and the loader, not memory, bounded the kernel:
+// ncu showed the epilogue warps waiting on the stage barrier, 0.65 ms per cfg3 sweep launch against 0.49 ms unstaged.)
+constexpr int S_STREAMS = 13;                          // SWEEP: i f g o c h | c_{t-1} | lambda_i f g o c | lambda_h (t = T only)
+constexpr int S_ROW_BYTES = BM * 4;                    // 128 samples of one unit
+constexpr int S_STAGE_BYTES = S_STREAMS * 4 * S_ROW_BYTES;     // 26 KB
+constexpr int S_STAGES = 3;
+
+// number of streams of a launch
+template <int MODE>
+__device__ __forceinline__ int staged_streams(const GateGemmArgs& p) {
+  if (MODE == GG_SWEEP) return p.last ? 13 : 12;
+  if (MODE == GG_MOMENTS) return 12;                   // lambda_g, gate_g, stored z_g
+  return p.z_accumulate ? 12 : 8;                      // GRAD: lambda_g, gate_g (, stored z_g)
+}
+// One tile of the staged epilogue for the calling warp (lane quarter `quarter`, unit group `ugrp`): 16 unit-steps, each
+// waits for its stage, copies its 8..13 inputs to registers, releases the stage and then computes / stores exactly like
+// epilogue_units (same closed forms, same store policy).  `sit` = running stage counter of this CTA.
+template <int MODE>
+__device__ __forceinline__ void epilogue_staged(const GateGemmArgs& p, uint32_t t_row, int ugrp, int quarter, int lane, int j0,
+                                                int64_t n, bool ok, int tl, float (&msum)[5], const uint8_t* sring,
+                                                uint64_t* sfull, uint64_t* sempty, uint32_t& sit) {
+  constexpr int JC = Cfg::JC;
+  const int H = p.H;
+  const int64_t ldn = p.ldn;
+  const Rho rho = p.rho;
+  const uint32_t ldn32 = (uint32_t)ldn;
+  const int u0 = ugrp * (JC / 4);
+  const uint32_t row0 = (uint32_t)((int64_t)tl * p.s_tstride + (int64_t)(j0 + u0) * ldn + n);
+  const uint32_t zrow0 = (uint32_t)(((int64_t)(j0 + u0) * p.zT + p.zt0 + tl) * ldn + n);
+  const uint32_t zstep = (uint32_t)((int64_t)p.zT * ldn);
+  const int64_t zgate = (int64_t)H * p.zT * ldn;
+  const uint32_t srow0 = (uint32_t)(((int64_t)(j0 + u0) * p.tc + tl) * ldn + n);
+  const uint32_t sstep = (uint32_t)((int64_t)p.tc * ldn);
+  const int64_t sgate = (int64_t)H * p.tc * ldn;
+  const float rho_g[4] = {rho.i, rho.f, rho.g, rho.o};
+  const float inv_rho_g[4] = {1.0f / rho.i, 1.0f / rho.f, 1.0f / rho.g, 1.0f / rho.o};
+  const float r_scale = (MODE == GG_GRAD && p.r16_hi) ? ldexpf(1.0f, cap_exp(*p.r_bound)) : 1.0f;
+  const float acc_scale = *p.acc_scale;
+  const uint32_t my = (uint32_t)(ugrp * BM + quarter * 32 + lane);       // float index of this thread inside a stream block
+#pragma unroll 1
+  for (int jb = 0; jb < JC / 4; jb += 8) {
+    float z[4][8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      tmem_ld8(t_row + g * JC + u0 + jb, z[g]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[g][i] *= acc_scale;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e, ++sit) {
+      const uint32_t st = sit % S_STAGES;
+      mbar_wait(&sfull[st], (sit / S_STAGES) & 1);
+      const float* sp = reinterpret_cast<const float*>(sring + st * S_STAGE_BYTES) + my;
+      const uint32_t ju = (uint32_t)(jb + e);
+      const uint32_t off = row0 + ju * ldn32, zoff = zrow0 + ju * zstep, soff = srow0 + ju * sstep;
+      if (MODE == GG_SWEEP) {
+        float in[13];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) in[q] = sp[q * (4 * BM)];
+        in[12] = p.last ? sp[12 * (4 * BM)] : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sempty[st]);            // values are in registers: the loader may refill the stage
+        SweepPoint sp_;
+        sp_.zi = z[0][e]; sp_.zf = z[1][e]; sp_.zg = z[2][e]; sp_.zo = z[3][e];
+        sp_.i = in[0]; sp_.f = in[1]; sp_.g = in[2]; sp_.o = in[3]; sp_.c = in[4]; sp_.h = in[5];
+        sp_.c_prev = in[6];
+        sp_.li = in[7]; sp_.lf = in[8]; sp_.lg = in[9]; sp_.lo = in[10]; sp_.lc = in[11]; sp_.lh = in[12];
+        const SweepResult r = sweep_point<FastMath>(sp_, rho, p.last != 0);
+        __stcs(p.gate[0] + off, r.i); __stcs(p.gate[1] + off, r.f); __stcs(p.gate[2] + off, r.g);
+        __stcs(p.gate[3] + off, r.o);
+        p.gate[4][off] = r.c;                                // c_t is read again by the next timestep
+        if (!p.last) {
+          p.gate[5][off] = r.h;
+          store_h16(p.h16_hi + off, p.h16_lo + off, r.h);
+        }
+        __stcs(p.dual[0] + off, r.li); __stcs(p.dual[1] + off, r.lf); __stcs(p.dual[2] + off, r.lg);
+        __stcs(p.dual[3] + off, r.lo); __stcs(p.dual[4] + off, r.lc);
+        if (p.zstore) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) __stcs(p.zstore + g * zgate + zoff, z[g][e]);
+        }
+        if (ok) { msum[0] += r.prim_sq; msum[1] += r.dual_sq; msum[2] += r.penalty; }
+        if (p.xbound_track)
+          msum[4] = fmaxf(fmaxf(fmaxf(msum[4], fmaf(fabsf(r.li), inv_rho_g[0], fabsf(r.i))),
+                                fmaxf(fmaf(fabsf(r.lf), inv_rho_g[1], fabsf(r.f)), fmaf(fabsf(r.lg), inv_rho_g[2], fabsf(r.g)))),
+                          fmaf(fabsf(r.lo), inv_rho_g[3], fabsf(r.o)));
+      } else {                                               // GG_GRAD
+        float lam[4], gv[4], zold[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          lam[g] = sp[g * (4 * BM)];
+          gv[g] = sp[(4 + g) * (4 * BM)];
+          zold[g] = p.z_accumulate ? sp[(8 + g) * (4 * BM)] : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sempty[st]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float u;
+          const float zz = z[g][e] + zold[g];
+          const float rr = grad_point<FastMath>(zz, lam[g], gv[g], rho_g[g], g == 2, &u);
+          const float rv = ok ? rr : 0.f;
+          if (ok) msum[g] += u * u;
+          if (p.bound_track) msum[4] = fmaxf(msum[4], 1.0f + fabsf(lam[g]) * inv_rho_g[g] + fabsf(gv[g]));
+          if (p.zstore) __stcs(p.zstore + g * zgate + zoff, zz);
+          if (p.r16_hi) {
+            split_f16(rv * r_scale, p.r16_hi + g * sgate + soff, p.r16_lo + g * sgate + soff);
+          } else {
+            *(p.scratch + g * sgate + soff) = rv;
+            if (p.scratch_q) *(p.scratch_q + g * sgate + soff) = tf32_lo(rv);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MOMENTS epilogue (GateGemmArgs::mom_*): the moment pass of the backtracking probes fused behind the Q = A_src G GEMM.
+// Inputs come through the staged ring exactly like the GRAD refresh (lambda_g, gate_g, stored z_g); Q is read from TMEM.
+// Per thread 28 fp32 partial sums (4 gates x F0, B1..B6) live for ONE tile (16 unit-steps); after each tile a transposed
+// warp reduction leaves sum i on lane i, which keeps its own fp64 total for the whole launch (two registers instead of
+// 28 doubles), added to fk_acc once at the end.
+__device__ __forceinline__ float tmem_ld1(uint32_t addr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(addr));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// v[i] (i < 32) summed over the 32 lanes; the total of index i ends up in v[0] of lane i
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = upper ? v[i] : v[i + w];
+      const float keep = upper ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+}
+
+// exact residual of one candidate: the activations of probe_eval.cu (two MUFU ops, <= 2 ulp)
+__device__ __forceinline__ float moments_exact_u(bool is_g, float z, float lr, float gv) {
+  const float a = is_g ? FastMath::tanh(z) : FastMath::sigmoid(z);
+  return (a - lr) - gv;
+}
+
+__device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t t_row, int ugrp, int quarter, int lane, bool ok,
+                                                 float (&qm)[4], double& macc, double& pacc, const uint8_t* sring,
+                                                 uint64_t* sfull, uint64_t* sempty, uint32_t& sit) {
+  constexpr int JC = Cfg::JC;
+  const int u0 = ugrp * (JC / 4);
+  const float acc_scale = *p.acc_scale;
+  const uint32_t my = (uint32_t)(ugrp * BM + quarter * 32 + lane);
+  const float rho_g[4] = {p.rho.i, p.rho.f, p.rho.g, p.rho.o};
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll 1
+  for (int jj = 0; jj < JC / 4; ++jj, ++sit) {
+    float q[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) q[g] = tmem_ld1(t_row + g * JC + u0 + jj);
+    const uint32_t st = sit % S_STAGES;
+    mbar_wait(&sfull[st], (sit / S_STAGES) & 1);
+    const float* sp = reinterpret_cast<const float*>(sring + st * S_STAGE_BYTES) + my;
+    float lam[4], gv[4], z0[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      lam[g] = sp[g * (4 * BM)];
+      gv[g] = sp[(4 + g) * (4 * BM)];
+      z0[g] = sp[(8 + g) * (4 * BM)];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sempty[st]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float rho = rho_g[g];
+      const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
+      const float lr = rho_pow2 ? lam[g] * (1.0f / rho) : __fdiv_rn(lam[g], rho);
+      const float qv = q[g] * acc_scale;
+      const float s = (g == 2) ? FastMath::tanh(z0[g]) : FastMath::sigmoid(z0[g]);
+      const float u = (s - lr) - gv[g];
+      float c[6];
+      moment_terms(g == 2, s, u, c);
+      const float t = ok ? qv * __int_as_float((127 - p.mom_k0[g]) << 23) : 0.f;       // Q 2^-k0; ghost rows contribute nothing
+      const float t2 = t * t, t3 = t2 * t;
+      float* a = acc + g * 8;
+      a[0] = fmaf(ok ? u : 0.f, u, a[0]);
+      a[1] = fmaf(c[0], t, a[1]);
+      a[2] = fmaf(c[1], t2, a[2]);
+      a[3] = fmaf(c[2], t3, a[3]);
+      a[4] = fmaf(c[3] * t2, t2, a[4]);
+      a[5] = fmaf(c[4] * t2, t3, a[5]);
+      a[6] = fmaf(c[5] * t3, t3, a[6]);
+      if (ok) qm[g] = fmaxf(qm[g], fabsf(qv));
+    }
+    if (ugrp == 0 && jj == 0) {
+      // lower-bound proofs below the expansion: candidates k < mom_pc[g] evaluated exactly on this one unit of the tile
+      float v[32];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float rho = rho_g[g];
+        const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
+        const float lr = rho_pow2 ? lam[g] * (1.0f / rho) : __fdiv_rn(lam[g], rho);
+        const float qv = q[g] * acc_scale;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float r = 0.f;
+          if (k < p.mom_pc[g]) {
+            const float uu = moments_exact_u(g == 2, fmaf(qv, __int_as_float((127 - k) << 23), z0[g]), lr, gv[g]);
+            r = ok ? uu * uu : 0.f;
+          }
+          v[g * 8 + k] = r;
+        }
+      }
+      warp_transpose_sum(v, lane);
+      pacc += (double)v[0];
+    }
+  }
+  warp_transpose_sum(acc, lane);
+  macc += (double)acc[0];
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM walks the tiles of the launch (unit tile fastest, so that the CTAs running at
 // the same time share A tiles in L2).  The accumulator is double-buffered in TMEM (2 x 256 columns): while the 16
 // epilogue warps (512 threads, 16 units each) drain tile i, the MMA warp already accumulates tile i+1 from a 4-stage
 // TMA ring, so the epilogue of a tile is hidden behind the next tile's MMAs instead of behind a second CTA.
-constexpr int P_STAGES = 4;
+// STAGED (SWEEP, h-phase GRAD): a third service warp (the state loader above) and a 3-stage state ring next to a 3-stage
+// operand ring (3 x 48 KB + 3 x 26 KB = 222 KB of the 227 KB); otherwise a 4-stage operand ring and no loader.
 constexpr int P_EPI_WARPS = 16;
-constexpr int P_THREADS = (2 + P_EPI_WARPS) * 32;     // 576
-constexpr int P_SMEM_BYTES = P_STAGES * Cfg::STAGE_BYTES + 1024;
+template <bool STAGED> struct PCfg {
+  static constexpr int STAGES = STAGED ? 3 : 4;
+  static constexpr int EPI_W0 = STAGED ? 3 : 2;                          // first epilogue warp
+  static constexpr int THREADS = (EPI_W0 + P_EPI_WARPS) * 32;            // 608 / 576
+  static constexpr int SMEM_BYTES = STAGES * Cfg::STAGE_BYTES + (STAGED ? S_STAGES * S_STAGE_BYTES : 0) + 1024;
+};
 
-template <int MODE>
-__global__ void __launch_bounds__(P_THREADS, 1)
-gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps maps, int slab0, const TcRange rng,
-                        int n_jt, int n_nt, int n_tiles) {
+template <int MODE, bool STAGED>
+__global__ void __launch_bounds__(PCfg<STAGED>::THREADS, 1)
+gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps maps, const __grid_constant__ StateMaps smaps,
+                        int slab0, const TcRange rng, int n_jt, int n_nt, int n_tiles) {
   using C = Cfg;
   constexpr int JC = C::JC;
+  constexpr int P_STAGES = PCfg<STAGED>::STAGES;
+  constexpr int EPI_W0 = PCfg<STAGED>::EPI_W0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sring = smem + P_STAGES * C::STAGE_BYTES;                      // state ring (STAGED only)
   __shared__ __align__(8) uint64_t full_bar[P_STAGES], empty_bar[P_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t sfull_bar[S_STAGES], sempty_bar[S_STAGES];
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[4 * P_EPI_WARPS];
 
@@ -399,12 +669,13 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
   const int nkb = rng.kb_end - rng.kb_begin;
   (void)H;
 
-  if (MODE == GG_RAWZ && p.done) {
+  if ((MODE == GG_RAWZ || MODE == GG_MOMENTS) && p.done) {
     if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], P_EPI_WARPS); }
+    for (int s = 0; s < S_STAGES; ++s) { mbar_init(&sfull_bar[s], 1); mbar_init(&sempty_bar[s], P_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
@@ -475,14 +746,51 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
         umma_commit(&tfull_bar[buf]);
       }
     }
+  } else if (STAGED && warp == 2) {
+    // ------------------------------------------------------------------ state loader (staged epilogue inputs)
+    const int ns = staged_streams<MODE>(p);
+    uint32_t sit = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int j0 = (tile % n_jt) * JC;
+      const int64_t n0 = (int64_t)((tile / n_jt) % n_nt) * BM;
+      const int tl = tile / (n_jt * n_nt);
+      for (int jj = 0; jj < JC / 4; ++jj, ++sit) {
+        const uint32_t st = sit % S_STAGES, round = sit / S_STAGES;
+        if (round > 0) mbar_wait(&sempty_bar[st], (round - 1) & 1);
+        uint8_t* dst = sring + st * S_STAGE_BYTES;
+        if (lane == 0) {
+          constexpr int SB = 4 * S_ROW_BYTES;               // bytes of one stream block: [4 unit groups][128 samples]
+          uint64_t* bar = &sfull_bar[st];
+          const int n0i = (int)n0, jg = j0 / (JC / 4), slab = slab0 + 1 + tl;
+          mbar_expect_tx(bar, (uint32_t)(ns * SB));
+          if (MODE == GG_SWEEP) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) tma_load_4d(dst + q * SB, &smaps.gate[q], bar, n0i, jj, jg, slab);
+            tma_load_4d(dst + 6 * SB, &smaps.gate[4], bar, n0i, jj, jg, slab - 1);           // c_{t-1}
+#pragma unroll
+            for (int q = 0; q < 5; ++q) tma_load_4d(dst + (7 + q) * SB, &smaps.dual[q], bar, n0i, jj, jg, slab);
+            if (ns > 12) tma_load_3d(dst + 12 * SB, &smaps.dual_h, bar, n0i, jj, jg);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tma_load_4d(dst + q * SB, &smaps.dual[q], bar, n0i, jj, jg, slab);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tma_load_4d(dst + (4 + q) * SB, &smaps.gate[q], bar, n0i, jj, jg, slab);
+            if (ns > 8) tma_load_5d(dst + 8 * SB, &smaps.zstore, bar, n0i, p.zt0 + tl, jj, jg, 0);
+          }
+        }
+        __syncwarp();
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..17)
-    const int ew = warp - 2;
+    // ------------------------------------------------------------------ epilogue (16 warps)
+    const int ew = warp - EPI_W0;
     const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
     const int ugrp = ew >> 2;                          // 4 warps per lane quarter: 16 of the tile's 64 units each
     const int row = quarter * 32 + lane;
     float msum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // [4] = running max of the |R| bound (GRAD, x-phase)
-    uint32_t ti = 0;
+    float qm[4] = {0.f, 0.f, 0.f, 0.f};             // MOMENTS: max |Q| per gate
+    double macc = 0.0, pacc = 0.0;                   // MOMENTS: this lane's moment / proof total (warp_transpose_sum)
+    uint32_t ti = 0, sit = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int j0 = (tile % n_jt) * JC;
       const int n0 = ((tile / n_jt) % n_nt) * BM;
@@ -492,7 +800,9 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * C::NCOL + ((uint32_t)(quarter * 32) << 16);
-      epilogue_units<MODE>(p, t_row, ugrp * (JC / 4), (ugrp + 1) * (JC / 4), j0, n, n < p.n, tl, msum);
+      if (MODE == GG_MOMENTS) epilogue_moments(p, t_row, ugrp, quarter, lane, n < p.n, qm, macc, pacc, sring, sfull_bar, sempty_bar, sit);
+      else if (STAGED) epilogue_staged<MODE>(p, t_row, ugrp, quarter, lane, j0, n, n < p.n, tl, msum, sring, sfull_bar, sempty_bar, sit);
+      else epilogue_units<MODE>(p, t_row, ugrp * (JC / 4), (ugrp + 1) * (JC / 4), j0, n, n < p.n, tl, msum);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -505,6 +815,28 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
       for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
       if (lane == 0) atomicMax(p.bound_track, __float_as_uint(b));
     }
+    if (MODE == GG_MOMENTS) {
+      // lane l of every warp holds the fp64 total of sum index l: (gate l / 8, moment or proof candidate l % 8)
+      const int g = lane >> 3, k = lane & 7;
+      if (k < 7) atomicAdd(p.fk_acc + g * ADMM_FK_SLOTS + ADMM_FK_MOMENTS + k, ldexp(macc, k * p.mom_k0[g]));   // B_k in units of Q^k
+      if (ugrp == 0 && k < p.mom_pc[g]) atomicAdd(p.fk_acc + g * ADMM_FK_SLOTS + ADMM_MAX_CAND + 1 + k, pacc);
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {
+        float m = qm[gg];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.qmax + gg), __float_as_uint(m));
+      }
+    }
+    if (MODE == GG_SWEEP && p.xbound_track) {
+      float b = msum[4];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+      if (lane == 0) {                                   // 1 + |lambda/rho| + |gate| >= |u| >= |R|
+        atomicMax(p.xbound_track, __float_as_uint(1.0f + b));          // the bound in force: only ever raised here
+        atomicMax(p.xbound_track + 1, __float_as_uint(1.0f + b));      // this sweep's own maximum (replaces [0] at t = T)
+      }
+    }
     if (MODE == GG_SWEEP || MODE == GG_GRAD) {
       double* dst = (MODE == GG_SWEEP) ? p.metrics : p.fw_acc;
       constexpr int NOUT = (MODE == GG_SWEEP) ? 3 : 4;
@@ -515,7 +847,7 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
           if (lane == 0) red[k * P_EPI_WARPS + ew] = sm_;
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        const int et = threadIdx.x - 64;
+        const int et = threadIdx.x - EPI_W0 * 32;
         if (et < NOUT) {
           double acc = 0.0;
 #pragma unroll
@@ -576,7 +908,10 @@ struct TcMeta {
   int s_x;                                        // x is stored as fp16 pairs of x 2^s_x
   float scale_z, scale_q, scale_d;                // 2^-(sa+sb): accumulator -> z (weights), Q (gradient), x dW (refresh)
   unsigned r_bound;                               // bound on |R| of the A^T R operand (bit pattern), see GateGemmArgs
-  int pad_[6];
+  // the same bound for the NEXT iteration, measured by the sweep over what it writes (xbound_track): [0] in force (raised
+  // as the sweep goes, so a partial sweep stays covered), [1] the running maximum of the current sweep, copied to [0] at t = T
+  unsigned x_bound[2];
+  int pad_[4];
 };
 
 // workspace layout in floats (fp16 buffers take half a float per element):
@@ -703,14 +1038,79 @@ int get_maps(const admm_problem* p, int grad_src, TcMaps* out) {
   return rc ? ADMM_ECUDA : ADMM_OK;
 }
 
-template <int MODE>
+// fp32 state maps (see StateMaps).  dims (ldn, 16, H/16, slabs), box (128, 1, 4, 1), no swizzle.
+int make_state_map(CUtensorMap* m, const float* base, uint64_t ldn, uint64_t H, uint64_t slabs) {
+  EncodeFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADMM_ECUDA; }
+  cuuint64_t dims[4] = {ldn, 16, H / 16, slabs};
+  cuuint64_t strides[3] = {ldn * 4, 16 * ldn * 4, H * ldn * 4};
+  cuuint32_t box[4] = {(cuuint32_t)BM, 1, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, slabs > 1 ? 4 : 3, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (state) failed (%d)", (int)r); return ADMM_ECUDA; }
+  return ADMM_OK;
+}
+int make_zstore_map(CUtensorMap* m, const float* base, uint64_t ldn, uint64_t H, uint64_t zT) {
+  EncodeFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADMM_ECUDA; }
+  cuuint64_t dims[5] = {ldn, zT, 16, H / 16, 4};
+  cuuint64_t strides[4] = {ldn * 4, zT * ldn * 4, 16 * zT * ldn * 4, H * zT * ldn * 4};
+  cuuint32_t box[5] = {(cuuint32_t)BM, 1, 1, 4, 4};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (zstore) failed (%d)", (int)r); return ADMM_ECUDA; }
+  return ADMM_OK;
+}
+
+struct StateKey {
+  const void *g[6], *d[5], *dh, *z;
+  int64_t ldn;
+  int T, H;
+  bool operator<(const StateKey& o) const {
+    return std::tie(g[0], g[1], g[2], g[3], g[4], g[5], d[0], d[1], d[2], d[3], d[4], dh, z, ldn, T, H) <
+           std::tie(o.g[0], o.g[1], o.g[2], o.g[3], o.g[4], o.g[5], o.d[0], o.d[1], o.d[2], o.d[3], o.d[4], o.dh, o.z, o.ldn, o.T, o.H);
+  }
+};
+std::map<StateKey, StateMaps> g_state_maps;
+
+// State maps of a problem (cached).  The admm_problem pointers are the tensors' bases; a launch addresses slabs through
+// the TMA coordinates.
+int get_state_maps(const admm_problem* p, StateMaps* out) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  StateKey key;
+  for (int q = 0; q < 6; ++q) key.g[q] = p->gate[q];
+  for (int q = 0; q < 5; ++q) key.d[q] = p->dual[q];
+  key.dh = p->dual_h; key.z = p->zstore; key.ldn = p->ldn; key.T = p->T; key.H = p->H;
+  auto it = g_state_maps.find(key);
+  if (it == g_state_maps.end()) {
+    if (g_state_maps.size() > 64) g_state_maps.clear();
+    StateMaps m;
+    memset(&m, 0, sizeof(m));
+    int rc = 0;
+    for (int q = 0; q < 6; ++q) rc |= make_state_map(&m.gate[q], p->gate[q], p->ldn, p->H, p->T + 1);
+    for (int q = 0; q < 5; ++q) rc |= make_state_map(&m.dual[q], p->dual[q], p->ldn, p->H, p->T + 1);
+    if (p->dual_h) rc |= make_state_map(&m.dual_h, p->dual_h, p->ldn, p->H, 1);
+    if (p->zstore) rc |= make_zstore_map(&m.zstore, p->zstore, p->ldn, p->H, p->T);
+    if (rc) return ADMM_ECUDA;
+    it = g_state_maps.emplace(key, m).first;
+  }
+  *out = it->second;
+  return ADMM_OK;
+}
+
+template <int MODE, bool STAGED = false>
 int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, int slab0, int tc, const TcRange& rng,
               cudaStream_t st, const char* label) {
   using C = Cfg;
   KernelScope ks_(label, st);
   static bool configured_p = false;
   if (!configured_p) {
-    cudaFuncSetAttribute(gate_gemm_tc_persistent<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    cudaFuncSetAttribute(gate_gemm_tc_persistent<MODE, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         PCfg<STAGED>::SMEM_BYTES);
     configured_p = true;
   }
   static int n_sm = 0;
@@ -722,7 +1122,15 @@ int launch_tc(const admm_problem* p, const GateGemmArgs& a, const TcMaps& maps, 
   const int n_jt = p->H / C::JC, n_nt = (int)(p->ldn / BM);
   const int n_tiles = n_jt * n_nt * tc;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  gate_gemm_tc_persistent<MODE><<<grid, P_THREADS, P_SMEM_BYTES, st>>>(a, maps, slab0, rng, n_jt, n_nt, n_tiles);
+  StateMaps smaps;
+  if (STAGED) {
+    const int rc = get_state_maps(p, &smaps);
+    if (rc) return rc;
+  } else {
+    memset(&smaps, 0, sizeof(smaps));
+  }
+  gate_gemm_tc_persistent<MODE, STAGED><<<grid, PCfg<STAGED>::THREADS, PCfg<STAGED>::SMEM_BYTES, st>>>(a, maps, smaps, slab0, rng,
+                                                                                                     n_jt, n_nt, n_tiles);
   count_launch();
   return check_launch("gate_gemm_tc_persistent");
 }
@@ -811,6 +1219,43 @@ int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStrea
 }
 
 unsigned* tc_r_bound(const admm_problem* p) { return &ws_meta(p)->r_bound; }
+unsigned* tc_x_bound(const admm_problem* p) { return ws_meta(p)->x_bound; }
+
+namespace {
+// max over t = 1..T, units and samples of 1 + |lambda_g/rho_g| + |gate_g| (g = i,f,g,o) -> out (bit pattern, atomicMax)
+__global__ void state_bound_kernel(const float* __restrict__ gate, const float* __restrict__ dual, float inv_rho, int64_t n,
+                                   unsigned* out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fmaf(fabsf(dual[i]), inv_rho, fabsf(gate[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(1.0f + m));
+}
+__global__ void set_u32_kernel(unsigned* dst, unsigned v0, unsigned v1) { dst[0] = v0; dst[1] = v1; }
+}  // namespace
+
+// x_bound from the state as it is (after the caller wrote gates / duals directly: admm_tc_refresh(ADMM_TC_STATE))
+int tc_refresh_bound(const admm_problem* p, cudaStream_t st) {
+  KernelScope ks_("tc_refresh_bound", st);
+  unsigned* xb = tc_x_bound(p);
+  if (!p->dual[0] || !p->gate[0]) return ADMM_OK;          // ADMM-LSTM-L problems carry no lambda_g here and track their own bound
+  if (cudaMemsetAsync(xb, 0, 2 * sizeof(unsigned), st) != cudaSuccess) return check_launch("x_bound memset");
+  const int64_t slab = (int64_t)p->H * p->ldn, n = (int64_t)p->T * slab;
+  for (int g = 0; g < 4; ++g) {
+    state_bound_kernel<<<prep_grid(n), 256, 0, st>>>(p->gate[g] + slab, p->dual[g] + slab, 1.0f / p->hp.rho[g], n, xb);
+    count_launch();
+  }
+  return check_launch("state_bound");
+}
+// x_bound of the forward initialisation: lambda = 0 and |gate| < 1  ->  2
+int tc_set_bound(const admm_problem* p, float v, cudaStream_t st) {
+  unsigned bits;
+  memcpy(&bits, &v, sizeof(bits));
+  set_u32_kernel<<<1, 1, 0, st>>>(tc_x_bound(p), bits, bits);
+  count_launch();
+  return check_launch("set_bound");
+}
 
 void tc_h16(const admm_problem* p, __half** hi, __half** lo) {
   const WsLayout w = ws_layout(p);
@@ -847,15 +1292,41 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
     return e ? atoi(e) : 1;
   }();
   a.epi_prefetch = epi_prefetch;
+  // Staged epilogue inputs (A/B switches for measurements).  GRAD (K = D: the epilogue IS the kernel): on, 41.9 -> 29.7 ms per
+  // cfg3 step, 89 % of the copy bandwidth.  SWEEP: off -- there the full-K operand stream (3.3 GB per launch from L2) plus
+  // the state traffic sits at the L2 -> SM delivery limit either way (0.49 ms staged with a 3-stage operand ring, 0.49 ms
+  // unstaged with 4 stages; profiles/r02_ncu_sweep_staged_vs_unstaged.txt), so the variant with the deeper operand ring stays.
+  static const int epi_staged = [] {
+    const char* e = getenv("ADMM_EPI_STAGED");
+    return e ? atoi(e) : 1;
+  }();
+  static const int epi_staged_sweep = [] {
+    const char* e = getenv("ADMM_EPI_STAGED_SWEEP");
+    return e ? atoi(e) : 0;
+  }();
   const int nkx = (p->D + BK - 1) / BK, nkh = (p->H + BK - 1) / BK;
   const TcRange full{0, nkx + nkh, 0};
   switch (mode) {
     case GG_FORWARD: return launch_tc<GG_FORWARD>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<FORWARD>");
-    case GG_SWEEP: return launch_tc<GG_SWEEP>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<SWEEP>");
+    case GG_SWEEP:
+      if (epi_staged_sweep) return launch_tc<GG_SWEEP, true>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<SWEEP>");
+      return launch_tc<GG_SWEEP>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<SWEEP>");
     case GG_GRAD:
-      if (z_refresh) return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, TcRange{0, nkx, 1}, st, "gate_gemm_tc<GRAD:z+=x*dW>");
+      if (z_refresh) {
+        if (epi_staged) return launch_tc<GG_GRAD, true>(p, a, maps, slab0, tc, TcRange{0, nkx, 1}, st, "gate_gemm_tc<GRAD:z+=x*dW>");
+        return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, TcRange{0, nkx, 1}, st, "gate_gemm_tc<GRAD:z+=x*dW>");
+      }
+      if (epi_staged) return launch_tc<GG_GRAD, true>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<GRAD:full>");
       return launch_tc<GG_GRAD>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<GRAD:full>");
     case GG_RAWZ: return launch_tc<GG_RAWZ>(p, a, maps, slab0, tc, full, st, "gate_gemm_tc<RAWZ:z>");
+    case GG_MOMENTS: {
+      // Q = A_src G in TMEM, moment sums in the epilogue (needs the z store as Z0)
+      GateGemmArgs q = a;
+      q.acc_scale = &meta->scale_q;
+      const TcRange qr = (a.src == ADMM_SRC_X) ? TcRange{0, nkx, 1} : TcRange{nkx, nkx + nkh, 1};
+      return launch_tc<GG_MOMENTS, true>(p, q, maps, slab0, tc, qr, st,
+                                         a.src == ADMM_SRC_X ? "gate_gemm_tc<MOMENTS:Q=x*G>" : "gate_gemm_tc<MOMENTS:Q=h*G>");
+    }
     case GG_PROBE: {
       // Z0 = x W + h U, then Q = A_src G: two launches of the same kernel (each keeps the 64-unit tile and
       // two resident CTAs per SM; a fused Z0|Q tile needs all 512 TMEM columns and halves the tile width)

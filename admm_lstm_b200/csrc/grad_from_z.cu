@@ -14,12 +14,28 @@ namespace {
 
 constexpr int NT = 256;
 
+// same operand scaling as the tensor-core epilogues (gate_gemm_tc.cu cap_exp / split_f16)
+__device__ __forceinline__ int g_cap_exp(unsigned max_bits) {
+  const float m = __uint_as_float(max_bits);
+  if (!(m > 0.f) || !isfinite(m)) return 0;
+  int e;
+  frexpf(m, &e);
+  return 13 - e;
+}
+__device__ __forceinline__ void g_split(float vs, __half* hi, __half* lo) {
+  const float c = fminf(fmaxf(vs, -65504.0f), 65504.0f);
+  const __half h = __float2half_rn(c);
+  *hi = h;
+  *lo = __float2half_rn(c - __half2float(h));
+}
+
 __global__ void __launch_bounds__(NT) grad_from_z_kernel(const GradFromZArgs p, int n_nb, int64_t items_per_gate) {
   __shared__ float red[NT / 32];
   const int g = blockIdx.y;
   const float rho = p.rho[g];
   float fsum = 0.f, bmax = 0.f;
   const float inv_rho = 1.0f / rho;
+  const float r_scale = p.r16_hi ? ldexpf(1.0f, g_cap_exp(*p.r_bound)) : 1.0f;
   for (int64_t item = blockIdx.x; item < items_per_gate; item += gridDim.x) {
     const int nb = (int)(item % n_nb);
     const int64_t row = item / n_nb;                 // (unit j, timestep tl)
@@ -43,8 +59,16 @@ __global__ void __launch_bounds__(NT) grad_from_z_kernel(const GradFromZArgs p, 
       if (ok) fsum = fmaf(u, u, fsum);
       bmax = fmaxf(bmax, 1.0f + fabsf(lam[e]) * inv_rho + fabsf(gv[e]));     // >= |u| >= |R| for any z
     }
-    *reinterpret_cast<float4*>(p.r + ro) = make_float4(r[0], r[1], r[2], r[3]);       // re-read at once by atr: keep in L2
-    *reinterpret_cast<float4*>(p.r_lo + ro) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+    if (p.r16_hi) {
+      __align__(8) __half hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) g_split(r[e] * r_scale, &hi[e], &lo[e]);
+      *reinterpret_cast<uint2*>(p.r16_hi + ro) = *reinterpret_cast<const uint2*>(hi);      // re-read at once by atr: keep in L2
+      *reinterpret_cast<uint2*>(p.r16_lo + ro) = *reinterpret_cast<const uint2*>(lo);
+    } else {
+      *reinterpret_cast<float4*>(p.r + ro) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(p.r_lo + ro) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+    }
   }
   if (p.bound_track) {
 #pragma unroll

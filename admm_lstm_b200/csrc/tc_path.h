@@ -16,6 +16,9 @@ int tc_refresh_wx_delta(const admm_problem* p, cudaStream_t st);
 int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a, int tc, cudaStream_t st);
 int atr_tc(const admm_problem* p, const AtrArgs& a, cudaStream_t st);
 unsigned* tc_r_bound(const admm_problem* p);     // device slot: bound on |R| of the fp16 A^T R operand (bit pattern)
+unsigned* tc_x_bound(const admm_problem* p);     // device slots [2]: the same bound for the next iteration, measured by the sweep
+int tc_refresh_bound(const admm_problem* p, cudaStream_t st);      // ... recomputed from the state as it is
+int tc_set_bound(const admm_problem* p, float v, cudaStream_t st);
 void tc_h16(const admm_problem* p, __half** hi, __half** lo);   // fp16 pair of h 2^11, [T+1][H][ldn] each
 
 // capi.cu helpers shared with admm_l.cu

@@ -425,20 +425,22 @@ def kernel_table(kern, ksteps, opt, T, D, H, peaks, ms_step):
     model = {
         "gate_gemm_tc<SWEEP>": ((22 + z) * H * 4 + D * 4, 8.0 * H * (D + H), "sweep: gate GEMM + i,f,g,o,c,h + duals (a5-a10)"),
         "gate_gemm_simt_kernel": ((22 + z) * H * 4 + D * 4, 8.0 * H * (D + H), "CUDA-core gate GEMM (all modes)"),
-        "grad_from_z_kernel": (20.0 * H * 4, 0.0, "x-phase residual R from stored z (reads z,lambda,gate; writes R hi/lo)"),
+        "grad_from_z_kernel": (16.0 * H * 4, 0.0, "x-phase residual R from stored z (reads z,lambda,gate; writes R as an fp16 pair)"),
         "atr_tc<64,tf32>": (8.0 * H * 4 + 2 * D * 4, 8.0 * H * D, "x-phase G = x^T R (3xTF32)"),
+        "atr_tc<64,f16>": (4.0 * H * 4 + D * 4, 8.0 * H * D, "x-phase G = x^T R (fp16 pairs)") if D <= 64 else (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase G = h^T R (fp16 pairs)"),
         "atr_tc<128,tf32>": (8.0 * H * 4 + 2 * D * 4, 8.0 * H * D, "x-phase G = x^T R (3xTF32)"),
         "atr_tc<256,tf32>": (8.0 * H * 4 + 2 * D * 4, 8.0 * H * D, "x-phase G = x^T R (3xTF32)"),
         "gate_gemm_tc<RAWZ:Q=x*G>": (4.0 * H * 4 + D * 4, 8.0 * H * D, "x-phase probe operand Q = x G"),
         "gate_gemm_tc<RAWZ:Q=h*G>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase probe operand Q = h G"),
         "gate_gemm_tc<RAWZ:z>": (4.0 * H * 4 + (D + H) * 4, 8.0 * H * (D + H), "pre-activations (no z store)"),
-        "probe_moments_kernel": (2 * 16.0 * H * 4, 0.0, "moment pass of both phases (reads z0,Q,lambda,gate)"),
+        "probe_moments_kernel": (2 * 16.0 * H * 4, 0.0, "moment pass of both phases, unfused (reads z0,Q,lambda,gate)"),
+        "gate_gemm_tc<MOMENTS:Q=x*G>": (12.0 * H * 4 + D * 4, 8.0 * H * D, "x-phase probes: Q = x G in TMEM + moment sums + proofs (reads z0,lambda,gate)"),
+        "gate_gemm_tc<MOMENTS:Q=h*G>": (12.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase probes: Q = h G in TMEM + moment sums + proofs (reads z0,lambda,gate)"),
         "probe_eval_kernel": (0.0, 0.0, "exact / lower-bound candidate passes (subset of the units)"),
         "gate_gemm_tc<GRAD:z+=x*dW>": (20.0 * H * 4 + D * 4, 8.0 * H * D, "h-phase: z += x dW, residual R as fp16 pair"),
         "gate_gemm_tc<GRAD:full>": (12.0 * H * 4 + (D + H) * 4, 8.0 * H * (D + H), "gradient pass with its own GEMM (no valid z store)"),
         "atr_tc<256,f16>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase G = h^T R (fp16 pairs)"),
         "atr_tc<128,f16>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase G = h^T R (fp16 pairs)"),
-        "atr_tc<64,f16>": (4.0 * H * 4 + H * 4, 8.0 * H * H, "h-phase G = h^T R (fp16 pairs)"),
     }
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -704,6 +706,8 @@ def main():
             "step_tflops_useful": step_flops / (ms_step * 1e-3) / 1e12,
             "kernel_ms_per_step": {k: round(v[1] / ksteps, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},
             "step_metrics": metrics, "theta_trace": opt.theta_trace(), "per_step_ms": per_step_ms,
+            "probe_qmax": {"x": [float(v) for v in opt._qmax_w[:4].tolist()], "h": [float(v) for v in opt._qmax_w[4:].tolist()],
+                           "note": "max |Q| = max |A_src G| per gate of the last step: the perturbation of the pre-activations at theta = 1"},
         }
         if world == 1 and not args.no_cpu_baseline:
             # one warm-up step first: the first iteration from the forward-initialised state leaves the backtracking

@@ -16,6 +16,17 @@ class Comm:
         self.group = group
         self.world_size = dist.get_world_size(group) if self.active else 1
         self.rank = dist.get_rank(group) if self.active else 0
+        self.events = None            # set by enable_timing()
+
+    def _reduce(self, t: torch.Tensor, op) -> None:
+        if self.events is not None and t.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(t, op=op, group=self.group)
+            e1.record()
+            self.events.append((t.numel() * t.element_size(), e0, e1))
+        else:
+            dist.all_reduce(t, op=op, group=self.group)
 
     def allreduce_sum_(self, *tensors: torch.Tensor) -> None:
         """In-place sum over ranks.  Identical reduced values on every rank keep the replicated
@@ -23,14 +34,35 @@ class Comm:
         if not self.active:
             return
         for t in tensors:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self._reduce(t, dist.ReduceOp.SUM)
 
     def allreduce_max_(self, *tensors: torch.Tensor) -> None:
         """In-place maximum over ranks (the global torch.max scalars of ADMM-LSTM-L, admm_lstm.py:168,179,225)."""
         if not self.active:
             return
         for t in tensors:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._reduce(t, dist.ReduceOp.MAX)
+
+    def enable_timing(self, enabled: bool = True) -> None:
+        """Bracket every collective with CUDA events on the launching stream: the elapsed time of a collective is its
+        transfer plus the wait for the slowest rank to arrive -- the evidence for what limits multi-GPU scaling."""
+        self.events = [] if enabled else None
+
+    def timing_summary(self):
+        """{'calls', 'ms', 'bytes', 'ms_small' (payload <= 64 KB), 'ms_large'} of the recorded collectives; synchronises."""
+        torch.cuda.synchronize()
+        out = {"calls": 0, "ms": 0.0, "bytes": 0, "calls_small": 0, "ms_small": 0.0, "ms_large": 0.0}
+        for nbytes, e0, e1 in self.events or []:
+            ms = e0.elapsed_time(e1)
+            out["calls"] += 1
+            out["ms"] += ms
+            out["bytes"] += nbytes
+            if nbytes <= 65536:
+                out["calls_small"] += 1
+                out["ms_small"] += ms
+            else:
+                out["ms_large"] += ms
+        return out
 
     def shard_range(self, n_total: int) -> Tuple[int, int]:
         """Contiguous, balanced slice [lo, hi) of n_total samples owned by this rank."""

@@ -40,6 +40,7 @@ struct LSlot {
   const float* P;        // [4][H][ldn] = x W + h_{s-1} U
   __half* h16_hi;        // fp16 pair of h 2^11 at slot s (the gate GEMM's A operand), or nullptr
   __half* h16_lo;
+  unsigned* h_ovf;       // sticky flag: |h| >= 32 did not fit the fp16 pair (tc_h_overflow)
   float* next_max;       // [4]: max |gate_g - lambda_p,g/rho_p| of the values this iteration leaves at slot s, i.e. the
                          // torch.max of update_z / update_zg (admm_lstm.py:168,179) of the NEXT iteration -- measured when
                          // the values are written instead of by a separate pass over the state
@@ -50,6 +51,7 @@ struct LSlot {
 
 __device__ __forceinline__ void l_store_h_side(const LSlot& p, int64_t idx, float h) {
   if (!p.h16_hi) return;
+  if (!(fabsf(h * 2048.0f) <= 65504.0f)) *p.h_ovf = 1u;
   const float c = fminf(fmaxf(h * 2048.0f, -65504.0f), 65504.0f);       // 2^11 = SCALE_H of gate_gemm_tc.cu
   const __half hh = __float2half_rn(c);
   p.h16_hi[idx] = hh;
@@ -428,9 +430,10 @@ LSlot make_slot(const admm_l_problem* lp, int s, const float* P, float* next_max
   k.lam10 = lp->lam10 + (int64_t)s * slab;
   k.P = P;
   k.next_max = next_max;
-  k.h16_hi = k.h16_lo = nullptr; k.bound_track = nullptr;
+  k.h16_hi = k.h16_lo = nullptr; k.bound_track = nullptr; k.h_ovf = nullptr;
   if (b.tc_ws && tc_eligible(&b)) {
     k.bound_track = tc_r_bound(&b);
+    k.h_ovf = tc_h_overflow(&b);
     tc_h16(&b, &k.h16_hi, &k.h16_lo);
     k.h16_hi += (int64_t)s * slab;
     k.h16_lo += (int64_t)s * slab;

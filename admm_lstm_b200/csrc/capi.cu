@@ -473,6 +473,19 @@ int admm_tc_refresh(const admm_problem* p, int what, void* stream) {
   return ADMM_OK;
 }
 
+int admm_tc_overflow(const admm_problem* p, int reset, void* stream) {
+  int rc = validate(p, "admm_tc_overflow");
+  if (rc) return rc;
+  if (!(p->tc_ws && tc_eligible(p))) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned flag = 0;
+  if (cudaMemcpyAsync(&flag, tc_h_overflow(p), sizeof(flag), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return check_launch("admm_tc_overflow") ? ADMM_ECUDA : ADMM_ECUDA;
+  if (reset && flag && cudaMemsetAsync(tc_h_overflow(p), 0, sizeof(flag), st) != cudaSuccess) return check_launch("overflow reset");
+  return flag ? 1 : 0;
+}
+
 int admm_debug_preact(const admm_problem* p, int t, float* out, int use_tc, void* stream) {
   int rc = validate(p, "admm_debug_preact");
   if (rc) return rc;

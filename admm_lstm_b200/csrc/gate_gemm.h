@@ -41,6 +41,7 @@ struct GateGemmArgs {
   int32_t z_accumulate;  // GRAD: z = zstore + acc (acc = x (W_new - W_old)) instead of z = acc
   __half* h16_hi;        // slab t of the fp16 pair of h 2^11 (tensor-core path): the gate GEMM's A operand
   __half* h16_lo;
+  unsigned* h_ovf;       // sticky device flag: an |h| >= 2^16 / 2^11 was clamped when its fp16 pair was written (set by gate_gemm_tc)
   const float* acc_scale;  // tensor-core path: 2^-(sa+sb) that turns the accumulator of this launch into z or Q
   // GRAD on the tensor-core path.  x-phase: bound_track receives max (1 + |lambda/rho| + |gate|) >= |R| (bit pattern,
   // atomicMax).  h-phase: R^T is written as an fp16 pair of R 2^sR (sR from *r_bound) for the fp16 A^T R GEMM.

@@ -39,7 +39,10 @@ namespace {
 constexpr int BM = 128;        // samples per tile (UMMA M)
 constexpr int BK = 32;         // features per pipeline stage (2 UMMA k-steps of 16)
 constexpr int CHUNK_BYTES = 64 * BK * 2;     // one MN chunk: 64 halfs (128 B) x BK rows
-constexpr int SCALE_H = 11;    // h operand scale 2^11: |h| < 1 for t < T by construction, finite up to |h| < 32
+// h operand scale 2^11.  h_t = (rho_h o tanh(c) - lambda_h)/rho_h with o an unconstrained ADMM primal, so |h| < 1 is typical
+// (o stays near a sigmoid value) but NOT guaranteed; the fp16 pair represents |h| < 2^16 / 2^11 = 32 and saturates above.
+// A clamped value raises the sticky device flag TcMeta::h_overflow (admm_tc_overflow in the C ABI, opt.metrics()).
+constexpr int SCALE_H = 11;
 
 struct TcMaps {
   CUtensorMap x, x_lo, h, h_lo;         // fp16 hi / lo halves of x 2^sX and h 2^SCALE_H; dims (ldn, K, slabs)
@@ -185,8 +188,10 @@ __device__ __forceinline__ void split_f16(float vs, __half* hi, __half* lo) {
   *hi = h;
   *lo = __float2half_rn(c - __half2float(h));
 }
-__device__ __forceinline__ void store_h16(__half* hi, __half* lo, float h) {
-  split_f16(h * (float)(1 << SCALE_H), hi, lo);
+__device__ __forceinline__ void store_h16(__half* hi, __half* lo, float h, unsigned* ovf) {
+  const float vs = h * (float)(1 << SCALE_H);
+  if (!(fabsf(vs) <= 65504.0f)) *ovf = 1u;        // clamped (or NaN): the operand no longer represents h
+  split_f16(vs, hi, lo);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
@@ -279,7 +284,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             if (p.gate[3]) __stcs(p.gate[3] + off[e], r.o);
             __stcs(p.gate[4] + off[e], r.c);
             p.gate[5][off[e]] = r.h;
-            store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h);   // fp16 pair: the next timestep's A operand
+            store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h, p.h_ovf);   // fp16 pair: the next timestep's A operand
           }
         }
         if (MODE == GG_SWEEP) {
@@ -325,7 +330,7 @@ __device__ __forceinline__ void epilogue_units(const GateGemmArgs& p, uint32_t t
             p.gate[4][off[e]] = r.c;                         // c_t is read again by the next timestep
             if (!p.last) {
               p.gate[5][off[e]] = r.h;
-              store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h);
+              store_h16(p.h16_hi + off[e], p.h16_lo + off[e], r.h, p.h_ovf);
             }
             __stcs(p.dual[0] + off[e], r.li); __stcs(p.dual[1] + off[e], r.lf); __stcs(p.dual[2] + off[e], r.lg);
             __stcs(p.dual[3] + off[e], r.lo); __stcs(p.dual[4] + off[e], r.lc);
@@ -475,7 +480,7 @@ __device__ __forceinline__ void epilogue_staged(const GateGemmArgs& p, uint32_t 
         p.gate[4][off] = r.c;                                // c_t is read again by the next timestep
         if (!p.last) {
           p.gate[5][off] = r.h;
-          store_h16(p.h16_hi + off, p.h16_lo + off, r.h);
+          store_h16(p.h16_hi + off, p.h16_lo + off, r.h, p.h_ovf);
         }
         __stcs(p.dual[0] + off, r.li); __stcs(p.dual[1] + off, r.lf); __stcs(p.dual[2] + off, r.lg);
         __stcs(p.dual[3] + off, r.lo); __stcs(p.dual[4] + off, r.lc);
@@ -911,7 +916,8 @@ struct TcMeta {
   // the same bound for the NEXT iteration, measured by the sweep over what it writes (xbound_track): [0] in force (raised
   // as the sweep goes, so a partial sweep stays covered), [1] the running maximum of the current sweep, copied to [0] at t = T
   unsigned x_bound[2];
-  int pad_[4];
+  unsigned h_overflow;                            // sticky: an h value did not fit its fp16 pair (store_h16)
+  int pad_[3];
 };
 
 // workspace layout in floats (fp16 buffers take half a float per element):
@@ -988,6 +994,7 @@ __global__ void prep_f16_kernel(int kind, const float* __restrict__ a, const flo
   const float sc = ldexpf(1.0f, ex);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = (b ? a[i] - b[i] : a[i]) * sc;
+    if (kind == PREP_H && !(fabsf(v) <= 65504.0f)) meta->h_overflow = 1u;
     split_f16(v, hi + i, lo + i);
   }
 }
@@ -1220,6 +1227,7 @@ int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStrea
 
 unsigned* tc_r_bound(const admm_problem* p) { return &ws_meta(p)->r_bound; }
 unsigned* tc_x_bound(const admm_problem* p) { return ws_meta(p)->x_bound; }
+unsigned* tc_h_overflow(const admm_problem* p) { return &ws_meta(p)->h_overflow; }
 
 namespace {
 // max over t = 1..T, units and samples of 1 + |lambda_g/rho_g| + |gate_g| (g = i,f,g,o) -> out (bit pattern, atomicMax)
@@ -1287,6 +1295,7 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   }
   const TcMeta* meta = ws_meta(p);
   a.acc_scale = z_refresh ? &meta->scale_d : &meta->scale_z;
+  a.h_ovf = &ws_meta(p)->h_overflow;
   static const int epi_prefetch = [] {          // on unless ADMM_EPI_PREFETCH=0 (A/B switch for measurements)
     const char* e = getenv("ADMM_EPI_PREFETCH");
     return e ? atoi(e) : 1;

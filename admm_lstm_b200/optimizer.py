@@ -98,6 +98,7 @@ class ADMMBasedOptimizer(object):
                    full data, as `torchrun demo.py` would; each keeps its contiguous slice) or
                    'presharded' (each rank passes only its own samples).
       use_tensor_cores  None = automatic (tcgen05 path when the shape is eligible).
+      use_cuda_graph  True: replay the step as one CUDA graph (launch-bound shapes; opt-in, see _graph_wanted).
       probe        how the backtracking loop of the weight updates (admm.py:331-338) gets f(w + G/theta): 'moments'
                    (default; one pass, every theta at once from a 6th-order expansion along the probe ray, valid where
                    the perturbation of the pre-activations is <= 2^-4 -- checked on the device, exact passes follow if
@@ -111,7 +112,7 @@ class ADMMBasedOptimizer(object):
                  variant: Optional[str] = None, with_dual_y: bool = False, sharding: str = "slice",
                  use_tensor_cores: Optional[bool] = None, scratch_bytes: Optional[int] = None,
                  comm: Optional[Comm] = None, keep_preactivations: Optional[bool] = None,
-                 probe: Optional[str] = None) -> None:
+                 probe: Optional[str] = None, use_cuda_graph: Optional[bool] = None) -> None:
         self._lib = _lib.load()
         self.device = _require_cuda()
         if self._lib.admm_device_ok() <= 0:
@@ -238,6 +239,11 @@ class ADMMBasedOptimizer(object):
                                  "h": self._materialize_dual_h, "y": lambda: self._dual_y.t()[:N]})
         self.last_metrics: Optional[Dict[str, float]] = None
         self.phase_events = None          # set by enable_phase_timing()
+        env_graph = os.environ.get("ADMM_LSTM_GRAPH")
+        self.use_cuda_graph = use_cuda_graph if use_cuda_graph is not None else (None if env_graph is None else env_graph != "0")
+        self._graphs: Dict[tuple, tuple] = {}
+        self.graph_replays = 0
+        self.graph_replayed_launches = 0          # kernels launched by graph replays (the library's counter sees only the capture)
         self.__initialize_primal_gates()
         self._set_z_valid(True)           # the forward pass stored z of the initial weights and states
 
@@ -463,6 +469,10 @@ class ADMMBasedOptimizer(object):
                     if not math.isfinite(q) or q >= 2.0 ** (_lib.ADMM_MAX_CAND - 7):
                         return full          # a diverging run: the expansion's window would not fit, go straight to the exact passes
                     k0[g] = int(math.ceil(math.log2(q * 32.0)))    # <= ADMM_MAX_CAND - 2, so the proofs (k0 + 2) fit
+        if self.use_cuda_graph:
+            # the plan is baked into a captured graph: one common, even k0 for the four gates changes rarely (a larger k0 is
+            # always valid, it only moves candidates from the expansion to the lower-bound proofs)
+            k0 = [min(_lib.ADMM_MAX_CAND - 2, (max(k0) + 1) // 2 * 2)] * 4
         # proofs always cover two exponents more than the hint asks for (ncand = 2): max|Q| may grow by 8x between the
         # hint and this step before the exact passes are needed
         return [(tuple(k0), 2, 1, 1)] + full
@@ -481,10 +491,20 @@ class ADMMBasedOptimizer(object):
     # ------------------------------------------------------------------------------------ step
     def step(self) -> None:
         """One ADMM iteration (admm.py:62-78)."""
-        st = _stream_ptr()
-        pp = self._pp
         self._resync_weights_if_replaced()
         self._poll_theta_hint()
+        if self._graph_wanted():
+            self._step_graphed()
+        else:
+            self._step_body(_stream_ptr())
+        self._set_z_valid(True)           # the sweep's GEMMs left z of the new weights / states in zstore
+        self._push_theta_hint()
+        self._step_index += 1
+
+    def _step_body(self, st) -> None:
+        """Everything a step enqueues on the stream: Wy, the weights, the sweep, the t = T tail.  No host synchronisation,
+        no allocation -- which is what makes it capturable as a CUDA graph."""
+        pp = self._pp
         self._mark("begin")
         self.__update_wy(st)
         self._mark("wy")
@@ -494,12 +514,39 @@ class ADMMBasedOptimizer(object):
         self._metrics.zero_()
         for t in range(1, self.seq_len + 1):
             self._call("admm_sweep_t", pp, t, self._metrics.data_ptr(), st)
-        self._set_z_valid(True)           # the sweep's GEMMs left z of the new weights / states in zstore
         self._mark("sweep")
         self.__update_last(st)
         self._mark("last")
-        self._push_theta_hint()
-        self._step_index += 1
+
+    # ------------------------------------------------------------------------------------ CUDA-graph replay (small shapes)
+    def _graph_wanted(self) -> bool:
+        """Launch-bound shapes (GoogleStock: ~100 launches of a few microseconds per step, admm.py:62-78 run as a Python
+        loop in the reference too) can replay the step as ONE CUDA graph: `use_cuda_graph=True` / ADMM_LSTM_GRAPH=1, after
+        three eager steps.  Not with sample sharding (the all-reduces stay eager) and not while per-call timing is recording."""
+        if self.comm.active or self.kernel_events is not None or self.phase_events is not None or self._step_index < 3:
+            return False
+        # Opt-in.  Measured on one B200 (profiles/r02_f_graph_vs_eager.txt): GoogleStock 0.47 ms per replayed step against
+        # 0.57 ms eager (the eager loop is bound by the host's ~45 launches, the replay by ~80 dependent nodes of a few
+        # microseconds each) -- but every change of the probe plan costs a re-capture (~15 ms), so over 50 steps eager wins.
+        return bool(self.use_cuda_graph)
+
+    def _step_graphed(self) -> None:
+        # what the captured launches bake in besides device pointers: the z_valid flag and the probe plans (by value)
+        key = (int(self._p.z_valid), tuple(self._probe_plans(_lib.SRC_X)), tuple(self._probe_plans(_lib.SRC_H)))
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            graph = torch.cuda.CUDAGraph()
+            before = int(self._lib.admm_launch_count(0))
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                self._step_body(_stream_ptr())
+            entry = (graph, int(self._lib.admm_launch_count(0)) - before)
+            self._graphs[key] = entry
+        entry[0].replay()
+        self.graph_replays += 1
+        self.graph_replayed_launches += entry[1]
 
     def __update_wy(self, st) -> None:
         """admm.py:246-280 / admm.no_dual_y.py:226-249."""
@@ -634,8 +681,21 @@ class ADMMBasedOptimizer(object):
         loss = float(m[3]) / self.n_global
         out = {"objective": loss + float(reg) + float(m[2]), "primal_residual": float(m[0]) ** 0.5,
                "dual_residual": float(m[1]) ** 0.5, "loss_term": loss}
+        if self.operand_overflow():
+            warning("An |h| >= 32 did not fit the fp16-pair operand of the tensor-core path: the iterates since are invalid. "
+                    "Re-create the optimizer with use_tensor_cores=False for this problem.")
         self.last_metrics = out
         return out
+
+    def operand_overflow(self, reset: bool = False) -> bool:
+        """Sticky device flag of the tensor-core path: some h_t (= (rho_h o tanh c - lambda_h)/rho_h, admm.py:455-457; o is an
+        unconstrained ADMM primal) reached |h| >= 32 and was clamped in the fp16-pair GEMM operand.  Synchronises."""
+        if self._tc_ws is None:
+            return False
+        rc = self._lib.admm_tc_overflow(self._pp, int(reset), _stream_ptr())
+        if rc < 0:
+            _lib.check(rc, "admm_tc_overflow")
+        return rc == 1
 
     def training_loss(self) -> float:
         """MSE of the model on the WHOLE (global) training set -- what demo.py:341 computes every epoch with model(train_x) --

@@ -595,6 +595,7 @@ def main():
     if args.kernel_timing == "inline":
         opt.enable_kernel_timing(True)
     lib.admm_launch_count(1)
+    replayed0 = opt.graph_replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -607,7 +608,8 @@ def main():
     e1.record()
     barrier()
     per_step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(args.steps)]
-    launches = int(lib.admm_launch_count(0))
+    # kernels launched in the timed region: the library's counter plus those inside replayed CUDA graphs (small shapes)
+    launches = int(lib.admm_launch_count(0)) + (opt.graph_replayed_launches - replayed0)
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     ksteps = args.steps
     if args.kernel_timing == "separate":
@@ -622,12 +624,27 @@ def main():
     # per-KERNEL timing (CUDA events recorded by the library around every launch, admm_kernel_timing) in two more steps
     kern = {}
     if args.kernel_timing != "off":
+        graph_setting, opt.use_cuda_graph = opt.use_cuda_graph, False      # event records do not belong inside a graph
         lib.admm_kernel_timing(1)
         for _ in range(2):
             opt.step()
         barrier()
         kern = kernel_report(lib)
         lib.admm_kernel_timing(0)
+        opt.use_cuda_graph = graph_setting
+    # what the collectives cost (transfer + waiting for the slowest rank), two more steps
+    comm_info = None
+    if world > 1:
+        opt.comm.enable_timing(True)
+        for _ in range(2):
+            opt.step()
+        barrier()
+        cs = opt.comm.timing_summary()
+        opt.comm.enable_timing(False)
+        comm_info = {"collectives_per_step": cs["calls"] // 2, "ms_per_step": round(cs["ms"] / 2, 3),
+                     "bytes_per_step": cs["bytes"] // 2, "small_calls_per_step": cs["calls_small"] // 2,
+                     "ms_small_per_step": round(cs["ms_small"] / 2, 3), "ms_large_per_step": round(cs["ms_large"] / 2, 3),
+                     "note": "CUDA-event time of every all-reduce on rank 0 (transfer + wait for the slowest rank)"}
 
     # ---- timed region 2: end to end through the public API with host buffers --------------------------
     pinned = {"wx": torch.empty((4, D, H)).pin_memory(), "wh": torch.empty((4, H, H)).pin_memory(),
@@ -701,7 +718,8 @@ def main():
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": n_total * T / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "comm": comm_info,
+            "cuda_graph": {"replays": opt.graph_replays, "graphs": len(opt._graphs)},
             "tensor_cores": bool(opt.uses_tensor_cores),
             "step_tflops_useful": step_flops / (ms_step * 1e-3) / 1e12,
             "kernel_ms_per_step": {k: round(v[1] / ksteps, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},

@@ -207,6 +207,13 @@ int admm_last_apply(const admm_problem* p, const float* theta, double* metrics, 
 int64_t admm_tc_workspace_bytes(const admm_problem* p);
 int admm_tc_refresh(const admm_problem* p, int what, void* stream);
 
+/* Tensor-core path only: the fp16-pair operand of h (h 2^11 as hi + lo halves) represents |h| < 32.  h_t = (rho_h o tanh c -
+ * lambda_h)/rho_h (admm.py:455-457) is below 1 in magnitude while o stays near a sigmoid value, but o is an unconstrained
+ * ADMM primal: a larger value is clamped in the OPERAND (the fp32 state keeps it) and raises a sticky device flag.
+ * Returns 1 if the flag is set, 0 if not (or no tensor-core workspace), negative on error; synchronises the stream;
+ * reset != 0 clears it.  A set flag means the pre-activations computed since are wrong: use the CUDA-core path. */
+int admm_tc_overflow(const admm_problem* p, int reset, void* stream);
+
 /* Test hook: out[4][H][ldn] = pre-activations z_g = x_t W_g + h_{t-1} U_g at timestep t, through the
  * tensor-core path (use_tc != 0, needs tc_ws) or the CUDA-core path. */
 int admm_debug_preact(const admm_problem* p, int t, float* out, int use_tc, void* stream);

@@ -635,3 +635,61 @@ def test_forward_takes_the_library_kernel_with_grad_enabled():
     m2 = LSTM(d, h, o).cuda()
     out = m2(xc)
     assert out.requires_grad
+
+
+@pytest.mark.parametrize("shape,tc", [((4224, 10, 1, 10, 1), False), ((384, 4, 16, 64, 1), True)])
+def test_cuda_graph_replay_equals_eager(shape, tc):
+    """Launch-bound shapes replay the step (admm.py:62-78: Wy, eight weights, T sweep launches, tail) as one CUDA graph; the
+    iterates must be those of the eager launches, also across a change of the probe plan (re-capture) and after the state
+    was written from outside (z_valid in the graph key)."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    n, t, d, h, o = shape
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=41)
+    _, a = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=tc, use_cuda_graph=True)
+    _, b = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=tc, use_cuda_graph=False)
+    for it in range(10):
+        a.step()
+        b.step()
+        if it == 6:
+            a.state_changed()
+            b.state_changed()
+    assert a.graph_replays >= 6 and b.graph_replays == 0
+    assert a.graph_replayed_launches > 0
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert rel_err(wa[k], wb[k]) < 1e-6, (k, rel_err(wa[k], wb[k]))
+    for k in ("i", "f", "g", "o", "c", "h"):
+        assert rel_err(a.gates[k].cpu().numpy(), b.gates[k].cpu().numpy()) < 1e-6, k
+    assert a.theta_trace() == b.theta_trace()
+    ma, mb = a.metrics(), b.metrics()
+    for k in ma:
+        assert abs(ma[k] - mb[k]) <= 1e-6 * abs(mb[k]) + 1e-12, k
+
+
+def test_h_operand_overflow_is_flagged():
+    """The fp16-pair operand of h on the tensor-core path holds |h| < 32.  h_t = o tanh(c) - lambda_h/rho_h with o an
+    unconstrained ADMM primal (admm.py:373-386, 455-457): a larger value must raise the sticky device flag instead of
+    silently clamping."""
+    _need_gpu()
+    from gpu_utils import make_opt
+    n, t, d, h, o = 256, 3, 16, 64, 1
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=3)
+    _, opt = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    opt.step()
+    assert not opt.operand_overflow()
+    # (1) the sweep writes it: lambda_o = -100 makes o ~ 100 (gate_prox), h = o tanh(c) far beyond 32
+    opt._dual["o"][1, :, : n] = -100.0
+    opt.state_changed()
+    assert not opt.operand_overflow()
+    opt.step()
+    assert float(opt.gates["h"].abs().max()) > 32.0
+    assert opt.operand_overflow(reset=True)
+    assert not opt.operand_overflow()
+    # (2) the state refresh sees it: h written from outside
+    opt._state["h"][1, :, : n] = 50.0
+    opt.state_changed()
+    assert opt.operand_overflow()
+    # the CUDA-core path has no such limit
+    _, ref = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=False)
+    assert not ref.operand_overflow()

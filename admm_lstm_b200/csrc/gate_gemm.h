@@ -56,10 +56,10 @@ struct GateGemmArgs {
   unsigned* xbound_track;
   // MOMENTS (tensor-core path with a valid z store): the probe operand Q = A_src G stays in TMEM and the epilogue accumulates
   // the moment sums of admm_probe_plan::moments straight from it (Q never goes to HBM): fk_acc[g][ADMM_FK_MOMENTS + 0..6],
-  // qmax[g], and -- on ONE unit per 64-unit tile, a rigorous lower bound like the 1/8 subsets of the unfused path -- the exact
+  // qmax[g], and -- on 1/8 of the units, a rigorous lower bound like the subsets of the unfused path -- the exact
   // sums of the candidates k < mom_pc[g] into fk_acc[g][ADMM_MAX_CAND + 1 + k].  mom_k0 = the plan's k0 (normalisation of Q).
   int32_t mom_k0[4];
-  int32_t mom_pc[4];     // proof candidates per gate, <= 8
+  int32_t mom_pc[4];     // proof candidates per gate, <= 16
   double* fk_acc;
   float* qmax;
 };

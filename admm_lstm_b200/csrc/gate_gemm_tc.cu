@@ -558,7 +558,7 @@ __device__ __forceinline__ float moments_exact_u(bool is_g, float z, float lr, f
 }
 
 __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t t_row, int ugrp, int quarter, int lane, bool ok,
-                                                 float (&qm)[4], double& macc, double& pacc, const uint8_t* sring,
+                                                 float (&qm)[4], double& macc, double (&pacc)[2], const uint8_t* sring,
                                                  uint64_t* sfull, uint64_t* sempty, uint32_t& sit) {
   constexpr int JC = Cfg::JC;
   const int u0 = ugrp * (JC / 4);
@@ -608,27 +608,36 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
       a[6] = fmaf(c[5] * t3, t3, a[6]);
       if (ok) qm[g] = fmaxf(qm[g], fabsf(qv));
     }
-    if (ugrp == 0 && jj == 0) {
-      // lower-bound proofs below the expansion: candidates k < mom_pc[g] evaluated exactly on this one unit of the tile
-      float v[32];
+    if ((jj & 7) == 0) {
+      // lower-bound proofs below the expansion: the candidates k < mom_pc[g] (<= 16) evaluated exactly on a subset of the units
+      // (any subset sum of squares is a lower bound of f).  The four candidates next to the expansion (k >= k0 - 2), where
+      // f(beta) exceeds est() by the smallest factor, on units 0 and 8 of every unit group = 1/8 of the units like the unfused
+      // path; the ones further below, where f grows ~4x per exponent, on one unit per tile.  Two gates per reduction.
+      const bool dense_all = (ugrp == 0 && jj == 0);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float rho = rho_g[g];
-        const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
-        const float lr = rho_pow2 ? lam[g] * (1.0f / rho) : __fdiv_rn(lam[g], rho);
-        const float qv = q[g] * acc_scale;
+      for (int half = 0; half < 2; ++half) {
+        if (p.mom_pc[2 * half] <= 0 && p.mom_pc[2 * half + 1] <= 0) continue;
+        float v[32];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float r = 0.f;
-          if (k < p.mom_pc[g]) {
-            const float uu = moments_exact_u(g == 2, fmaf(qv, __int_as_float((127 - k) << 23), z0[g]), lr, gv[g]);
-            r = ok ? uu * uu : 0.f;
+        for (int gg = 0; gg < 2; ++gg) {
+          const int g = 2 * half + gg;
+          const float rho = rho_g[g];
+          const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
+          const float lr = rho_pow2 ? lam[g] * (1.0f / rho) : __fdiv_rn(lam[g], rho);
+          const float qv = q[g] * acc_scale;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float r = 0.f;
+            if (k < p.mom_pc[g] && (dense_all || k >= p.mom_k0[g] - 2)) {
+              const float uu = moments_exact_u(g == 2, fmaf(qv, __int_as_float((127 - k) << 23), z0[g]), lr, gv[g]);
+              r = ok ? uu * uu : 0.f;
+            }
+            v[gg * 16 + k] = r;
           }
-          v[g * 8 + k] = r;
         }
+        warp_transpose_sum(v, lane);
+        pacc[half] += (double)v[0];
       }
-      warp_transpose_sum(v, lane);
-      pacc += (double)v[0];
     }
   }
   warp_transpose_sum(acc, lane);
@@ -794,7 +803,7 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
     const int row = quarter * 32 + lane;
     float msum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // [4] = running max of the |R| bound (GRAD, x-phase)
     float qm[4] = {0.f, 0.f, 0.f, 0.f};             // MOMENTS: max |Q| per gate
-    double macc = 0.0, pacc = 0.0;                   // MOMENTS: this lane's moment / proof total (warp_transpose_sum)
+    double macc = 0.0, pacc[2] = {0.0, 0.0};         // MOMENTS: this lane's moment / proof totals (warp_transpose_sum)
     uint32_t ti = 0, sit = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int j0 = (tile % n_jt) * JC;
@@ -824,7 +833,11 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
       // lane l of every warp holds the fp64 total of sum index l: (gate l / 8, moment or proof candidate l % 8)
       const int g = lane >> 3, k = lane & 7;
       if (k < 7) atomicAdd(p.fk_acc + g * ADMM_FK_SLOTS + ADMM_FK_MOMENTS + k, ldexp(macc, k * p.mom_k0[g]));   // B_k in units of Q^k
-      if (ugrp == 0 && k < p.mom_pc[g]) atomicAdd(p.fk_acc + g * ADMM_FK_SLOTS + ADMM_MAX_CAND + 1 + k, pacc);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {           // proofs: lane l holds candidate l % 16 of gate 2 half + l / 16
+        const int pg = 2 * half + (lane >> 4), pk = lane & 15;
+        if (pk < p.mom_pc[pg]) atomicAdd(p.fk_acc + pg * ADMM_FK_SLOTS + ADMM_MAX_CAND + 1 + pk, pacc[half]);
+      }
 #pragma unroll
       for (int gg = 0; gg < 4; ++gg) {
         float m = qm[gg];

@@ -253,7 +253,15 @@ def bench_admm_l(args, rank, world, local_rank, config, metric, unit):
     from admm_lstm_b200.admm_l import ADMMLOptimizer
     n_gpu, T, D, H, O, pname, cpu_n, cls = WORKLOADS[args.workload]
     n_gpu = args.n_per_gpu or n_gpu // 2            # 20 state tensors instead of 11 (+ zstore): half the samples fit
-    config.update({"samples_per_gpu": n_gpu, "O": 1, "hyper_parameters": "admm_l/main.py:111-129 as shipped"})
+    scaling = "weak"
+    if args.strong:
+        n_gpu, scaling = args.strong // max(world, 1), "strong"
+    config.update({"samples_per_gpu": n_gpu, "O": 1, "hyper_parameters": "admm_l/main.py:111-129 as shipped",
+                   "scaling_mode": scaling})
+    gpu_baseline = None
+    if world == 1 and not args.no_gpu_baseline:
+        gb_n = args.gpu_baseline_n or {"cfg3": 4096, "cfg2": 16384, "cfg4": 4096, "google": 4224, "small": 4096}[args.workload]
+        gpu_baseline = time_reference_gpu(args.workload, "admm_l", min(gb_n, n_gpu))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -299,6 +307,18 @@ def bench_admm_l(args, rank, world, local_rank, config, metric, unit):
     barrier()
     ksum = opt.kernel_time_summary()
     opt.enable_kernel_timing(False)
+    comm_info = None
+    if world > 1:
+        opt.comm.enable_timing(True)
+        for _ in range(2):
+            opt.step()
+        barrier()
+        cs = opt.comm.timing_summary()
+        opt.comm.enable_timing(False)
+        comm_info = {"collectives_per_step": cs["calls"] // 2, "ms_per_step": round(cs["ms"] / 2, 3),
+                     "bytes_per_step": cs["bytes"] // 2, "small_calls_per_step": cs["calls_small"] // 2,
+                     "ms_small_per_step": round(cs["ms_small"] / 2, 3), "ms_large_per_step": round(cs["ms_large"] / 2, 3),
+                     "note": "CUDA-event time of every all-reduce on rank 0 (transfer + wait for the slowest rank)"}
     pinned = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in (("wx", opt._wx), ("wh", opt._wh), ("wy", opt._wy))}
     h2d = x_pin.numel() * 4 + y_pin.numel() * 4
     d2h = sum(v.numel() * 4 for v in pinned.values())
@@ -338,8 +358,8 @@ def bench_admm_l(args, rank, world, local_rank, config, metric, unit):
                         "note": "useful fp32-equivalent flops (2*5H*(D+H) per sample-timestep) against the measured dense "
                                 "bf16 peak; fp16-pair (3 MMAs per product) ceiling = peak/3"}
         line = {"metric": metric, "value": n_total * T / (ms_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "comm": comm_info,
                 "e2e": {"value": n_total * T / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "tensor_cores": bool(opt.uses_tensor_cores),
@@ -347,6 +367,8 @@ def bench_admm_l(args, rank, world, local_rank, config, metric, unit):
                 "thetas": {k: float(v) for k, v in opt.thetas.items()}}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = time_reference_cpu(args.workload, "admm_l", 1, 1, budget_s=24.0)
+        if gpu_baseline is not None:
+            line["gpu_baseline"] = gpu_baseline
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -725,7 +747,10 @@ def main():
             "kernel_ms_per_step": {k: round(v[1] / ksteps, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},
             "step_metrics": metrics, "theta_trace": opt.theta_trace(), "per_step_ms": per_step_ms,
             "probe_qmax": {"x": [float(v) for v in opt._qmax_w[:4].tolist()], "h": [float(v) for v in opt._qmax_w[4:].tolist()],
-                           "note": "max |Q| = max |A_src G| per gate of the last step: the perturbation of the pre-activations at theta = 1"},
+                           "note": "max |Q| = max |A_src G| per gate of the last step: the perturbation of the pre-activations at theta = 1",
+                           "diag_last_h_phase": [int(v) for v in opt._done.cpu().tolist()[4:12]],
+                           "diag_note": "per gate: 0 = decided by the moment pass; 1 = a lower-bound proof was not conclusive, 2 = window "
+                                        "exhausted, 3 = expansion not valid at k0 (exact passes followed); then the exponent concerned"},
         }
         if world == 1 and not args.no_cpu_baseline:
             # one warm-up step first: the first iteration from the forward-initialised state leaves the backtracking

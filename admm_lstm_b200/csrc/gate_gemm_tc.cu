@@ -609,30 +609,32 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
       if (ok) qm[g] = fmaxf(qm[g], fabsf(qv));
     }
     if ((jj & 7) == 0) {
-      // lower-bound proofs below the expansion: the candidates k < mom_pc[g] (<= 16) evaluated exactly on a subset of the units
-      // (any subset sum of squares is a lower bound of f).  The four candidates next to the expansion (k >= k0 - 2), where
-      // f(beta) exceeds est() by the smallest factor, on units 0 and 8 of every unit group = 1/8 of the units like the unfused
-      // path; the ones further below, where f grows ~4x per exponent, on one unit per tile.  Two gates per reduction.
-      const bool dense_all = (ugrp == 0 && jj == 0);
+      // Lower-bound proofs below the expansion (any subset sum of squares is a lower bound of f(beta_k)): the candidates
+      // k < mom_pc[g] (<= 16) evaluated exactly.  Every candidate below k0 on units 0 and 8 of every unit group = 1/8 of the
+      // units, the density of the unfused path -- the margin f(beta_k) / est_k does NOT grow below the expansion (f saturates,
+      // est keeps doubling; a 1/64 subset left gate o of the H = 256 workload undecided).  The two insurance candidates at
+      // and above k0 (needed only if max|Q| grew since the hint) on one unit per tile.  Eight candidates x four gates per
+      // transposed reduction; the second round only when a gate has more than eight.
+      const bool sparse_too = (ugrp == 0 && jj == 0);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        if (p.mom_pc[2 * half] <= 0 && p.mom_pc[2 * half + 1] <= 0) continue;
+        if (p.mom_pc[0] <= 8 * half && p.mom_pc[1] <= 8 * half && p.mom_pc[2] <= 8 * half && p.mom_pc[3] <= 8 * half) continue;
         float v[32];
 #pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          const int g = 2 * half + gg;
+        for (int g = 0; g < 4; ++g) {
           const float rho = rho_g[g];
           const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
           const float lr = rho_pow2 ? lam[g] * (1.0f / rho) : __fdiv_rn(lam[g], rho);
           const float qv = q[g] * acc_scale;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
+          for (int kk = 0; kk < 8; ++kk) {
+            const int k = 8 * half + kk;
             float r = 0.f;
-            if (k < p.mom_pc[g] && (dense_all || k >= p.mom_k0[g] - 2)) {
+            if (k < p.mom_pc[g] && (k < p.mom_k0[g] || sparse_too)) {
               const float uu = moments_exact_u(g == 2, fmaf(qv, __int_as_float((127 - k) << 23), z0[g]), lr, gv[g]);
               r = ok ? uu * uu : 0.f;
             }
-            v[gg * 16 + k] = r;
+            v[g * 8 + kk] = r;
           }
         }
         warp_transpose_sum(v, lane);
@@ -834,8 +836,8 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
       const int g = lane >> 3, k = lane & 7;
       if (k < 7) atomicAdd(p.fk_acc + g * ADMM_FK_SLOTS + ADMM_FK_MOMENTS + k, ldexp(macc, k * p.mom_k0[g]));   // B_k in units of Q^k
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {           // proofs: lane l holds candidate l % 16 of gate 2 half + l / 16
-        const int pg = 2 * half + (lane >> 4), pk = lane & 15;
+      for (int half = 0; half < 2; ++half) {           // proofs: lane l holds candidate 8 half + l % 8 of gate l / 8
+        const int pg = lane >> 3, pk = 8 * half + (lane & 7);
         if (pk < p.mom_pc[pg]) atomicAdd(p.fk_acc + pg * ADMM_FK_SLOTS + ADMM_MAX_CAND + 1 + pk, pacc[half]);
       }
 #pragma unroll

@@ -266,7 +266,7 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
     a.r16_lo = reinterpret_cast<__half*>(a.scratch_q);
   }
   if (use_tc && p->zstore && p->wx_prev) {
-    // x-phase: full GEMM, z kept; h-phase: z <- z + x (W_new - W_old), no full GEMM (DESIGN.md section 5)
+    // x-phase: full GEMM, z kept; h-phase: z <- z + x (W_new - W_old), no full GEMM (DESIGN.md section 2)
     a.zstore = p->zstore; a.zT = p->T; a.zt0 = t0;
     a.z_accumulate = (src == ADMM_SRC_H);
   }

@@ -62,7 +62,15 @@ def _feature_major(x: torch.Tensor, ldn: int, device) -> torch.Tensor:
 
 class _StateDict:
     """Read-only mapping that presents the feature-major device buffers in the reference's shapes
-    ([N, T+1, H] for i,f,g,o,c,h and their duals, [N, O] for a / y) as zero-copy views."""
+    ([N, T+1, H] for i,f,g,o,c,h and their duals, [N, O] for a / y) as zero-copy views.
+
+    Ownership: the reference's getters hand out private copies (admm.py:191-213, `.clone().detach()` on every read -- 18 244
+    clones per step).  Here `opt.gates[k]` ALIASES the optimizer's state: it changes with the next step(), and writing through
+    it changes the iteration (call opt.state_changed() afterwards).  `copy()` gives the reference's semantics."""
+
+    def copy(self):
+        """{key: private clone} -- what the reference's accessors return."""
+        return {k: g().clone() for k, g in self._getters.items()}
 
     def __init__(self, getters):
         self._getters = getters

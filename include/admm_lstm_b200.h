@@ -108,7 +108,7 @@ typedef struct admm_problem {
   int64_t tc_ws_bytes;
   /* Optional (tensor-core path only; NULL -> the pre-activations are recomputed in every pass):
    * zstore [4][H][T][ldn] keeps z = x W + h U of all timesteps between the passes of the weight phase, so the
-   * phase needs 4 instead of 7 full-size GEMM passes per step; wx_prev [4][D][H] is the copy of
+   * phase needs 3 instead of 7 full-size GEMM passes per step; wx_prev [4][D][H] is the copy of
    * x2g taken before its update, from which the h-phase refreshes zstore with x (W_new - W_old) only. */
   float* zstore;
   float* wx_prev;

@@ -55,6 +55,9 @@ def check_state(opt, d, k, rows=None, tol=1e-4, dual_atol=5e-6):
 
 @pytest.mark.parametrize("name,tc", [("l_traj_small", False), ("l_traj_h64", False), ("l_traj_h64", True)])
 def test_l_trajectory_vs_reference_fixture(name, tc):
+    """Fixtures: the reference's OWN update functions (admm_l/admm_lstm.py) called by tests/golden/make_golden_l.py in the order
+    of main.py:139-191 -- the driver loop is restated there (admm_l_demo returns only losses); the unmodified admm_l_demo itself
+    is exercised end to end by tests/test_gpu_callers.py::test_reference_comparison_runs_unchanged."""
     _need_gpu()
     d = np.load(os.path.join(GOLD, name + ".npz"))
     opt = make_opt(d, d["x"], d["y"], use_tensor_cores=tc)

@@ -180,8 +180,11 @@ def test_real_data_50_iterations_vs_reference_curves(dataset, variant, params):
                 assert float(np.max(np.abs(duals[k][:rows] - rec[f"it{it}_dual_{k}"]))) < 1e-3 * scale, (it, k)
     assert abs(tr - rec["train_loss"][50]) < 0.01 * rec["train_loss"][50]
     assert abs(va - rec["val_loss"][50]) < 0.01 * rec["val_loss"][50]
-    if dataset != "googlestock":
-        assert first_flip is None, first_flip          # no knife edge on these data: strict 1e-4 throughout
+    # With the default moment probes the decisions are the exact-arithmetic ones and no run flips: strict
+    # 1e-4 on every weight for all 50 iterations on both datasets and both variants.  (The candidate-by-candidate probes of
+    # probe='exact' flip one knife-edge decision on GoogleStock/admm; the looser branch above is for them.)
+    if dataset != "googlestock" or opt.probe == "moments":
+        assert first_flip is None, first_flip
     print(f"{dataset}/{variant}: worst weight rel err over 50 iterations = {worst:.2e}, first theta flip at {first_flip}")
 
 

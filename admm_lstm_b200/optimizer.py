@@ -249,6 +249,7 @@ class ADMMBasedOptimizer(object):
         self.phase_events = None          # set by enable_phase_timing()
         env_graph = os.environ.get("ADMM_LSTM_GRAPH")
         self.use_cuda_graph = use_cuda_graph if use_cuda_graph is not None else (None if env_graph is None else env_graph != "0")
+        self._copy_stream = self._x_stage = self._y_stage = self._stage_ready = self._stage_free = None   # prefetch_inputs()
         self._graphs: Dict[tuple, tuple] = {}
         self.graph_replays = 0
         self.graph_replayed_launches = 0          # kernels launched by graph replays (the library's counter sees only the capture)
@@ -388,14 +389,40 @@ class ADMMBasedOptimizer(object):
             out[name] = (n + 1, ms + e0.elapsed_time(e1))
         return out
 
-    def refresh_inputs(self, train_x: torch.Tensor, train_y: torch.Tensor) -> None:
-        """Re-upload this rank's samples from (pinned) host memory into the device layout -- the
-        host->device leg of the end-to-end measurement in bench.py."""
+    def prefetch_inputs(self, train_x: torch.Tensor, train_y: torch.Tensor) -> None:
+        """Start the host->device copy of the NEXT inputs (this rank's samples, pinned host memory) on a side stream into a
+        staging buffer, so that it overlaps the step in flight; a following `refresh_inputs()` without arguments installs
+        them.  Double buffering of the inputs: the samples the running step reads are not touched."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._x_stage = torch.empty((self.n_local,) + tuple(train_x.shape[1:]), dtype=torch.float32, device=self.device)
+            self._y_stage = torch.empty((self.n_local,) + tuple(train_y.shape[1:]), dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free is not None:
+                self._copy_stream.wait_event(self._stage_free)          # the previous install has read the staging buffers
+            self._x_stage.copy_(train_x, non_blocking=True)
+            self._y_stage.copy_(train_y, non_blocking=True)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_ready.record(self._copy_stream)
+
+    def refresh_inputs(self, train_x: Optional[torch.Tensor] = None, train_y: Optional[torch.Tensor] = None) -> None:
+        """Install new inputs for this rank's samples in the device layout: from (pinned) host memory -- the host->device leg
+        of the end-to-end measurement in bench.py -- or, without arguments, from the staging buffers a `prefetch_inputs`
+        call filled in the background."""
         n = self.n_local
-        xd = train_x.to(self.device, non_blocking=True)
-        yd = train_y.to(self.device, non_blocking=True)
+        if train_x is None:
+            log_assert(self._stage_ready is not None, "refresh_inputs() without arguments needs a prefetch_inputs() before it.")
+            torch.cuda.current_stream().wait_event(self._stage_ready)
+            xd, yd = self._x_stage, self._y_stage
+        else:
+            xd = train_x.to(self.device, non_blocking=True)
+            yd = train_y.to(self.device, non_blocking=True)
         self._x[:, :, :n].copy_(xd.permute(1, 2, 0))
         self._y[:, :n].copy_(yd.t())
+        if train_x is None:
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+            self._stage_ready = None
         self._set_z_valid(False)
         if self._tc_ws is not None:
             self._call("admm_tc_refresh", self._pp, _lib.TC_INPUTS, _stream_ptr())

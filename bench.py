@@ -676,9 +676,14 @@ def main():
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
-        opt.refresh_inputs(x_pin, y_pin)
+    # every step: its inputs come from pinned host memory (the upload of step s+1 is started on a side stream while step
+    # s runs -- input double buffering, opt.prefetch_inputs -- and installed before step s+1), its result goes back to the host
+    opt.prefetch_inputs(x_pin, y_pin)
+    for i in range(args.steps):
+        opt.refresh_inputs()
         opt.step()
+        if i + 1 < args.steps:
+            opt.prefetch_inputs(x_pin, y_pin)
         opt.export_weights(pinned)
         torch.cuda.current_stream().synchronize()      # the caller consumes the weights every step
     e3.record()

@@ -696,3 +696,26 @@ def test_h_operand_overflow_is_flagged():
     # the CUDA-core path has no such limit
     _, ref = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=False)
     assert not ref.operand_overflow()
+
+
+def test_prefetched_inputs_equal_direct_refresh():
+    """opt.prefetch_inputs() (side-stream upload into a staging buffer) + refresh_inputs() installs the same inputs as
+    refresh_inputs(x, y): the e2e path of bench.py double-buffers its uploads this way."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    n, t, d, h, o = 300, 4, 16, 64, 1
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=51)
+    x2, y2, _ = synthetic_problem(n, t, d, h, o, seed=52)
+    _, a = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    _, b = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)
+    xp, yp = torch.from_numpy(x2).pin_memory(), torch.from_numpy(y2).pin_memory()
+    a.step(); b.step()
+    a.prefetch_inputs(xp, yp)
+    a.step(); b.step()
+    a.refresh_inputs()
+    b.refresh_inputs(xp, yp)
+    for _ in range(2):
+        a.step(); b.step()
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert np.array_equal(wa[k], wb[k]), k

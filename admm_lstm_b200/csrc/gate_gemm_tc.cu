@@ -1317,17 +1317,20 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   }();
   a.epi_prefetch = epi_prefetch;
   // Staged epilogue inputs (A/B switches for measurements).  GRAD (K = D: the epilogue IS the kernel): on, 41.9 -> 29.7 ms per
-  // cfg3 step, 89 % of the copy bandwidth.  SWEEP: off -- there the full-K operand stream (3.3 GB per launch from L2) plus
-  // the state traffic sits at the L2 -> SM delivery limit either way (0.49 ms staged with a 3-stage operand ring, 0.49 ms
-  // unstaged with 4 stages; profiles/r02_ncu_sweep_staged_vs_unstaged.txt), so the variant with the deeper operand ring stays.
+  // cfg3 step, 89 % of the copy bandwidth.  SWEEP at H = 1024: off -- there the full-K operand stream (3.3 GB per launch from
+  // L2) plus the state traffic sits at the L2 -> SM delivery limit either way (0.49 ms staged with a 3-stage operand ring,
+  // 0.49 ms unstaged with 4 stages; profiles/r02_ncu_sweep_staged_vs_unstaged.txt), so the deeper operand ring stays.
   static const int epi_staged = [] {
     const char* e = getenv("ADMM_EPI_STAGED");
     return e ? atoi(e) : 1;
   }();
-  static const int epi_staged_sweep = [] {
+  static const int epi_staged_sweep_env = [] {       // -1: by shape
     const char* e = getenv("ADMM_EPI_STAGED_SWEEP");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
   }();
+  // by shape: with D + H <= 768 the operand stream is small next to the state traffic and the staged epilogue wins
+  // (cfg2 0.894 -> 0.774 ms per launch = 0.69 of HBM, cfg4 0.483 -> 0.409 ms = 0.66; profiles/r02_p_staged_sweep_by_shape.txt)
+  const int epi_staged_sweep = epi_staged_sweep_env >= 0 ? epi_staged_sweep_env : (p->D + p->H <= 768);
   const int nkx = (p->D + BK - 1) / BK, nkh = (p->H + BK - 1) / BK;
   const TcRange full{0, nkx + nkh, 0};
   switch (mode) {

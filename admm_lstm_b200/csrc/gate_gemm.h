@@ -54,6 +54,7 @@ struct GateGemmArgs {
   // (bit pattern, atomicMax).  Those are exactly what the next iteration's gradient passes read, so the bound on |R| that
   // scales the fp16 operand of A^T R is known before the x-phase starts and its R^T can be fp16 pairs too.
   unsigned* xbound_track;
+  int32_t tma_hint;      // tensor-core path: L2 evict_last hint on the weight-operand TMA loads (set by gate_gemm_tc)
   // MOMENTS (tensor-core path with a valid z store): the probe operand Q = A_src G stays in TMEM and the epilogue accumulates
   // the moment sums of admm_probe_plan::moments straight from it (Q never goes to HBM): fk_acc[g][ADMM_FK_MOMENTS + 0..6],
   // qmax[g], and -- on 1/8 of the units, a rigorous lower bound like the subsets of the unfused path -- the exact

@@ -91,6 +91,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy encodings: evict_last 0x14F0000000000000, evict_first 0x12F0...)
+__device__ __forceinline__ void tma_load_4d_hint(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
                                             int c4) {
   asm volatile(
@@ -726,8 +733,15 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
           const CUtensorMap* bl = rng.b_is_grad ? &maps.gx_lo : (is_x ? &maps.wx_lo : &maps.wh_lo);
           const int kb0 = rng.b_is_grad ? li * BK : k0;
           uint8_t* sb = st + 2 * C::A_BYTES;
-          tma_load_4d(sb, bh, &full_bar[s], 0, kb0, j0 / 64, 0);
-          tma_load_4d(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 64, 0);
+          if (p.tma_hint) {
+            // the weight operand (18 MB of fp16 pairs at H = 1024) is re-read by every sample tile: keep it in L2 against the
+            // state stream (1.8 GB per launch) flowing through
+            tma_load_4d_hint(sb, bh, &full_bar[s], 0, kb0, j0 / 64, 0, 0x14F0000000000000ull);
+            tma_load_4d_hint(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 64, 0, 0x14F0000000000000ull);
+          } else {
+            tma_load_4d(sb, bh, &full_bar[s], 0, kb0, j0 / 64, 0);
+            tma_load_4d(sb + C::B_BYTES, bl, &full_bar[s], 0, kb0, j0 / 64, 0);
+          }
         }
       }
     }
@@ -1311,6 +1325,11 @@ int gate_gemm_tc(int mode, const admm_problem* p, const GateGemmArgs& a_in, int 
   const TcMeta* meta = ws_meta(p);
   a.acc_scale = z_refresh ? &meta->scale_d : &meta->scale_z;
   a.h_ovf = &ws_meta(p)->h_overflow;
+  static const int tma_hint = [] {              // L2 evict_last hint on the weight-operand TMA loads (A/B switch)
+    const char* e = getenv("ADMM_TMA_HINT");
+    return e ? atoi(e) : 1;
+  }();
+  a.tma_hint = tma_hint;
   static const int epi_prefetch = [] {          // on unless ADMM_EPI_PREFETCH=0 (A/B switch for measurements)
     const char* e = getenv("ADMM_EPI_PREFETCH");
     return e ? atoi(e) : 1;

@@ -89,6 +89,7 @@ SIGNATURES = {
     "admm_tc_refresh": (C.c_int, [PP, C.c_int, vp]),
     "admm_debug_preact": (C.c_int, [PP, C.c_int, vp, C.c_int, vp]),
     "admm_tc_overflow": (C.c_int, [PP, C.c_int, vp]),
+    "admm_load_inputs": (C.c_int, [PP, vp, vp, vp]),
     "admm_launch_count": (C.c_int64, [C.c_int]),
     "admm_kernel_timing": (C.c_int, [C.c_int]),
     "admm_kernel_timing_report": (C.c_int64, [C.c_char_p, C.c_int64]),

@@ -279,7 +279,13 @@ int admm_weight_grad(const admm_problem* p, int src, int t0, int tc, float* scra
     e.s_tstride = a.s_tstride;
     e.r = a.scratch; e.r_lo = a.scratch_q; e.fw_acc = fw_acc; e.bound_track = nullptr;
     e.r16_hi = a.r16_hi; e.r16_lo = a.r16_lo; e.r_bound = a.r_bound;
+    // exactly one of the two passes runs, decided on the device: the streaming pass over the stored z unless the inputs were
+    // replaced by different values since it was written (admm_load_inputs), else the pass with its own GEMM (it rewrites z)
+    e.skip_if = tc_z_dirty(p);
     rc = grad_from_z(e, st);
+    if (rc) return rc;
+    a.run_if = tc_z_dirty(p);
+    rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
   } else {
     rc = run_gate_gemm(GG_GRAD, p, a, tc, st);
   }
@@ -437,6 +443,8 @@ int admm_sweep_t(const admm_problem* p, int t, double* metrics, void* stream) {
   if (rc || !use_tc || t != p->T) return rc;
   if (cudaMemcpyAsync(a.xbound_track, a.xbound_track + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
     return check_launch("x_bound publish");
+  // the sweep rewrote every stored pre-activation from the current inputs
+  if (cudaMemsetAsync(tc_z_dirty(p), 0, sizeof(int32_t), st) != cudaSuccess) return check_launch("z_dirty clear");
   return ADMM_OK;
 }
 
@@ -471,6 +479,20 @@ int admm_tc_refresh(const admm_problem* p, int what, void* stream) {
   if ((what & ADMM_TC_STATE) && (rc = tc_refresh_state(p, st))) return rc;
   if ((what & ADMM_TC_STATE) && (rc = tc_refresh_bound(p, st))) return rc;
   return ADMM_OK;
+}
+
+int admm_load_inputs(const admm_problem* p, const float* x_nm, const float* y_nm, void* stream) {
+  int rc = validate(p, "admm_load_inputs");
+  if (rc) return rc;
+  ADMM_REQUIRE(x_nm && y_nm, "admm_load_inputs: null inputs");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool use_tc = p->tc_ws && tc_eligible(p);
+  int32_t* changed = use_tc ? tc_z_dirty(p) : nullptr;
+  rc = tc_load_inputs(const_cast<float*>(p->x), x_nm, p->n, (int64_t)p->T * p->D, p->ldn, changed, st);
+  if (rc) return rc;
+  rc = tc_load_inputs(const_cast<float*>(p->y), y_nm, p->n, p->O, p->ldn, nullptr, st);
+  if (rc || !use_tc) return rc;
+  return tc_refresh_inputs(p, st);          // operand copies of x (and the weight scales tied to its scale)
 }
 
 int admm_tc_overflow(const admm_problem* p, int reset, void* stream) {

@@ -55,6 +55,10 @@ struct GateGemmArgs {
   // scales the fp16 operand of A^T R is known before the x-phase starts and its R^T can be fp16 pairs too.
   unsigned* xbound_track;
   int32_t tma_hint;      // tensor-core path: L2 evict_last hint on the weight-operand TMA loads (set by gate_gemm_tc)
+  // Device-side launch predicate (tensor-core path): when set, the kernel returns at once unless *run_if != 0.  The x-phase
+  // gradient pass launches BOTH the pass over stored pre-activations (grad_from_z, skip_if) and this GEMM pass (run_if) on
+  // the "inputs changed since the z store was written" flag, so re-installing identical inputs costs no host round trip.
+  const int32_t* run_if;
   // MOMENTS (tensor-core path with a valid z store): the probe operand Q = A_src G stays in TMEM and the epilogue accumulates
   // the moment sums of admm_probe_plan::moments straight from it (Q never goes to HBM): fk_acc[g][ADMM_FK_MOMENTS + 0..6],
   // qmax[g], and -- on 1/8 of the units, a rigorous lower bound like the subsets of the unfused path -- the exact
@@ -133,6 +137,7 @@ struct GradFromZArgs {
   __half* r16_hi;
   __half* r16_lo;
   const unsigned* r_bound;
+  const int32_t* skip_if;   // device flag: return at once when *skip_if != 0 (see GateGemmArgs::run_if)
 };
 int grad_from_z(const GradFromZArgs& a, cudaStream_t st);
 

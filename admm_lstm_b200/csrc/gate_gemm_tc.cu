@@ -692,6 +692,7 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
   const int nkb = rng.kb_end - rng.kb_begin;
   (void)H;
 
+  if (p.run_if && *p.run_if == 0) return;
   if ((MODE == GG_RAWZ || MODE == GG_MOMENTS) && p.done) {
     if (p.done[0] && p.done[1] && p.done[2] && p.done[3]) return;
   }
@@ -946,7 +947,8 @@ struct TcMeta {
   // as the sweep goes, so a partial sweep stays covered), [1] the running maximum of the current sweep, copied to [0] at t = T
   unsigned x_bound[2];
   unsigned h_overflow;                            // sticky: an h value did not fit its fp16 pair (store_h16)
-  int pad_[3];
+  int z_dirty;                                    // inputs were replaced by different values since the z store was written
+  int pad_[2];
 };
 
 // workspace layout in floats (fp16 buffers take half a float per element):
@@ -1257,6 +1259,40 @@ int tc_refresh_grad(const admm_problem* p, int src, const float* grad, cudaStrea
 unsigned* tc_r_bound(const admm_problem* p) { return &ws_meta(p)->r_bound; }
 unsigned* tc_x_bound(const admm_problem* p) { return ws_meta(p)->x_bound; }
 unsigned* tc_h_overflow(const admm_problem* p) { return &ws_meta(p)->h_overflow; }
+int32_t* tc_z_dirty(const admm_problem* p) { return &ws_meta(p)->z_dirty; }
+
+namespace {
+// Install new inputs: src [n][cols] (sample-major, as the reference holds x [N, T, D] and y [N, O]) -> dst [cols][ldn]
+// (feature-major), tiled transpose through shared memory; *changed is set when any value differs bitwise from what dst held.
+__global__ void load_inputs_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int64_t cols, int64_t ldn,
+                                   int32_t* changed) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  bool diff = false;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t nn = n0 + r, cc = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (nn < n && cc < cols) ? src[nn * cols + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t cc = c0 + r, nn = n0 + threadIdx.x;
+    if (cc < cols && nn < n) {
+      const float v = tile[threadIdx.x][r];
+      float* d = dst + cc * ldn + nn;
+      if (__float_as_uint(*d) != __float_as_uint(v)) { diff = true; *d = v; }
+    }
+  }
+  if (__any_sync(0xffffffffu, diff) && threadIdx.x == 0 && changed) *changed = 1;
+}
+}  // namespace
+
+int tc_load_inputs(float* dst, const float* src, int64_t n, int64_t cols, int64_t ldn, int32_t* changed, cudaStream_t st) {
+  KernelScope ks_("load_inputs_kernel", st);
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((cols + 31) / 32));
+  load_inputs_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, n, cols, ldn, changed);
+  count_launch();
+  return check_launch("load_inputs");
+}
 
 namespace {
 // max over t = 1..T, units and samples of 1 + |lambda_g/rho_g| + |gate_g| (g = i,f,g,o) -> out (bit pattern, atomicMax)

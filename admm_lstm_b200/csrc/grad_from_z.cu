@@ -31,6 +31,7 @@ __device__ __forceinline__ void g_split(float vs, __half* hi, __half* lo) {
 
 __global__ void __launch_bounds__(NT) grad_from_z_kernel(const GradFromZArgs p, int n_nb, int64_t items_per_gate) {
   __shared__ float red[NT / 32];
+  if (p.skip_if && *p.skip_if != 0) return;
   const int g = blockIdx.y;
   const float rho = p.rho[g];
   float fsum = 0.f, bmax = 0.f;

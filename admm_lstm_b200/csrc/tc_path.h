@@ -19,6 +19,8 @@ unsigned* tc_r_bound(const admm_problem* p);     // device slot: bound on |R| of
 unsigned* tc_x_bound(const admm_problem* p);     // device slots [2]: the same bound for the next iteration, measured by the sweep
 int tc_refresh_bound(const admm_problem* p, cudaStream_t st);      // ... recomputed from the state as it is
 int tc_set_bound(const admm_problem* p, float v, cudaStream_t st);
+int32_t* tc_z_dirty(const admm_problem* p);      // device flag: inputs changed since the z store was written
+int tc_load_inputs(float* dst, const float* src, int64_t n, int64_t cols, int64_t ldn, int32_t* changed, cudaStream_t st);
 unsigned* tc_h_overflow(const admm_problem* p);  // sticky device flag: an h value was clamped when its fp16 pair was written
 void tc_h16(const admm_problem* p, __half** hi, __half** lo);   // fp16 pair of h 2^11, [T+1][H][ldn] each
 

@@ -417,15 +417,17 @@ class ADMMBasedOptimizer(object):
         else:
             xd = train_x.to(self.device, non_blocking=True)
             yd = train_y.to(self.device, non_blocking=True)
-        self._x[:, :, :n].copy_(xd.permute(1, 2, 0))
-        self._y[:, :n].copy_(yd.t())
+        xd = xd.to(torch.float32).contiguous()
+        yd = yd.to(torch.float32).contiguous()
+        # one transposing kernel per tensor into the device layout; on the tensor-core path it also notes ON THE DEVICE whether
+        # x changed at all -- if not, the stored pre-activations stay valid (admm_load_inputs), so z_valid is left alone
+        self._call("admm_load_inputs", self._pp, xd.data_ptr(), yd.data_ptr(), _stream_ptr())
         if train_x is None:
             self._stage_free = torch.cuda.Event()
             self._stage_free.record()
             self._stage_ready = None
-        self._set_z_valid(False)
-        if self._tc_ws is not None:
-            self._call("admm_tc_refresh", self._pp, _lib.TC_INPUTS, _stream_ptr())
+        if self._tc_ws is None:
+            self._set_z_valid(False)
 
     def state_changed(self) -> None:
         """Call after writing the state or weight buffers directly (tests do): re-derives the tensor-core side

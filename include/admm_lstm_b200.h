@@ -207,6 +207,14 @@ int admm_last_apply(const admm_problem* p, const float* theta, double* metrics, 
 int64_t admm_tc_workspace_bytes(const admm_problem* p);
 int admm_tc_refresh(const admm_problem* p, int what, void* stream);
 
+/* Install new inputs for this shard from DEVICE buffers in the reference's layout (x_nm [n][T][D], y_nm [n][O], sample-major)
+ * into the feature-major p->x / p->y, and refresh the tensor-core operand copies of x.  On the tensor-core path the kernel
+ * also records, on the device, whether any value of x differs from what was installed before: if not, the stored
+ * pre-activations (zstore) stay valid and the next x-phase gradient pass keeps its streaming form -- re-installing identical
+ * inputs every step (an end-to-end loop that re-uploads its batch) costs one transposing copy, no GEMM pass and no host
+ * round trip.  Leave admm_problem::z_valid as it is across this call. */
+int admm_load_inputs(const admm_problem* p, const float* x_nm, const float* y_nm, void* stream);
+
 /* Tensor-core path only: the fp16-pair operand of h (h 2^11 as hi + lo halves) represents |h| < 32.  h_t = (rho_h o tanh c -
  * lambda_h)/rho_h (admm.py:455-457) is below 1 in magnitude while o stays near a sigmoid value, but o is an unconstrained
  * ADMM primal: a larger value is clamped in the OPERAND (the fp32 state keeps it) and raises a sticky device flag.

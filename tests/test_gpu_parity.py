@@ -719,3 +719,42 @@ def test_prefetched_inputs_equal_direct_refresh():
     wa, wb = weights_of(a), weights_of(b)
     for k in WKEYS:
         assert np.array_equal(wa[k], wb[k]), k
+
+
+def test_reinstalled_inputs_keep_or_drop_the_stored_preactivations():
+    """admm_load_inputs decides ON THE DEVICE whether the stored pre-activations survive new inputs: identical values ->
+    the run continues bit-identically to one that never re-installed them (streaming x-phase gradient); different values ->
+    the x-phase falls back to its GEMM pass and the iterates equal those of an optimizer that keeps no z store at all."""
+    _need_gpu()
+    from gpu_utils import make_opt, weights_of
+    n, t, d, h, o = 300, 4, 16, 64, 1
+    x, y, w = synthetic_problem(n, t, d, h, o, seed=61)
+    x2, y2, _ = synthetic_problem(n, t, d, h, o, seed=62)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    _, a = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)      # re-installs the same inputs every step
+    _, b = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True)      # never touches them
+    for _ in range(3):
+        a.refresh_inputs(xt, yt)
+        assert a._p.z_valid == 1
+        a.step()
+        b.step()
+    wa, wb = weights_of(a), weights_of(b)
+    for k in WKEYS:
+        assert np.array_equal(wa[k], wb[k]), k
+    assert int(a._done.cpu()[0]) == 1
+    # different inputs: against an optimizer without z store (every pass recomputes its pre-activations)
+    _, c = make_opt(w, x, y, GOOGLE, "admm", use_tensor_cores=True, keep_preactivations=False)
+    for _ in range(3):
+        c.step()
+    x2t, y2t = torch.from_numpy(x2), torch.from_numpy(y2)
+    a.refresh_inputs(x2t, y2t)
+    c.refresh_inputs(x2t, y2t)
+    for _ in range(2):
+        a.step()
+        c.step()
+    wa, wc = weights_of(a), weights_of(c)
+    # (c runs the unfused probe passes and full-GEMM gradient passes: other summation orders, hence 2e-5 and not bit equality)
+    for k in WKEYS:
+        assert rel_err(wa[k], wc[k]) < 2e-5, (k, rel_err(wa[k], wc[k]))
+    assert rel_err(a.gates["h"].cpu().numpy(), c.gates["h"].cpu().numpy()) < 2e-5
+    assert a.theta_trace() == c.theta_trace()

@@ -45,7 +45,7 @@ class Problem(C.Structure):
 
 class ProbePlan(C.Structure):
     _fields_ = [("k0", C.c_int32 * 4), ("ncand", C.c_int32), ("proof", C.c_int32), ("moments", C.c_int32),
-                ("reserved_", C.c_int32)]
+                ("order", C.c_int32)]
 
 
 class LHyper(C.Structure):

@@ -100,6 +100,31 @@ __device__ __forceinline__ void moment_terms(bool is_g, float s, float u, float 
 }
 #endif
 
+#if defined(__CUDACC__)
+// The same up to 4th order (c1..c4): valid for |d| <= 2^-6 at the accuracy moment_terms has for |d| <= 2^-4.
+__device__ __forceinline__ void moment_terms4(bool is_g, float s, float u, float (&c)[4]) {
+  float a1, a2, a3, a4;
+  if (is_g) {
+    const float t2 = s * s, d1 = 1.0f - t2;
+    a1 = d1;
+    a2 = -s * d1;
+    a3 = (-1.0f / 3.0f) * d1 * fmaf(-3.0f, t2, 1.0f);
+    a4 = (1.0f / 3.0f) * s * d1 * fmaf(-3.0f, t2, 2.0f);
+  } else {
+    const float d1 = s * (1.0f - s), m = fmaf(-2.0f, s, 1.0f), dm = d1 * m;
+    a1 = d1;
+    a2 = 0.5f * dm;
+    a3 = (1.0f / 6.0f) * d1 * fmaf(-6.0f, d1, 1.0f);
+    a4 = (1.0f / 24.0f) * dm * fmaf(-12.0f, d1, 1.0f);
+  }
+  const float u2 = 2.0f * u;
+  c[0] = u2 * a1;
+  c[1] = fmaf(u2, a2, a1 * a1);
+  c[2] = fmaf(u2, a3, 2.0f * a1 * a2);
+  c[3] = fmaf(u2, a4, fmaf(2.0f * a1, a3, a2 * a2));
+}
+#endif
+
 // admm.py:239-244, expressed through the activation value itself
 ADMM_HD float dsigmoid_from(float s) { return s * (1.0f - s); }
 ADMM_HD float dtanh_from(float t) { return 1.0f - t * t; }

@@ -354,6 +354,7 @@ int admm_weight_probe(const admm_problem* p, int src, int t0, int tc, float* scr
     bool ok = fused != 0;
     for (int g = 0; g < 4; ++g) {
       a.mom_k0[g] = plan->k0[g];
+      a.mom_order = (plan->order == 4) ? 4 : 6;
       a.mom_pc[g] = plan->proof ? plan->k0[g] + plan->ncand : 0;
       ok = ok && a.mom_pc[g] <= 16 && plan->k0[g] < 64;
     }

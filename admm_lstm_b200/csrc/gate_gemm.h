@@ -65,6 +65,7 @@ struct GateGemmArgs {
   // sums of the candidates k < mom_pc[g] into fk_acc[g][ADMM_MAX_CAND + 1 + k].  mom_k0 = the plan's k0 (normalisation of Q).
   int32_t mom_k0[4];
   int32_t mom_pc[4];     // proof candidates per gate, <= 16
+  int32_t mom_order;     // 6 or 4 (admm_probe_plan::order)
   double* fk_acc;
   float* qmax;
 };

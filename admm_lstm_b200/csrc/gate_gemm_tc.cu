@@ -564,6 +564,7 @@ __device__ __forceinline__ float moments_exact_u(bool is_g, float z, float lr, f
   return (a - lr) - gv;
 }
 
+template <int ORDER>
 __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t t_row, int ugrp, int quarter, int lane, bool ok,
                                                  float (&qm)[4], double& macc, double (&pacc)[2], const uint8_t* sring,
                                                  uint64_t* sfull, uint64_t* sempty, uint32_t& sit) {
@@ -601,18 +602,27 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
       const float qv = q[g] * acc_scale;
       const float s = (g == 2) ? FastMath::tanh(z0[g]) : FastMath::sigmoid(z0[g]);
       const float u = (s - lr) - gv[g];
-      float c[6];
-      moment_terms(g == 2, s, u, c);
       const float t = ok ? qv * __int_as_float((127 - p.mom_k0[g]) << 23) : 0.f;       // Q 2^-k0; ghost rows contribute nothing
       const float t2 = t * t, t3 = t2 * t;
       float* a = acc + g * 8;
       a[0] = fmaf(ok ? u : 0.f, u, a[0]);
-      a[1] = fmaf(c[0], t, a[1]);
-      a[2] = fmaf(c[1], t2, a[2]);
-      a[3] = fmaf(c[2], t3, a[3]);
-      a[4] = fmaf(c[3] * t2, t2, a[4]);
-      a[5] = fmaf(c[4] * t2, t3, a[5]);
-      a[6] = fmaf(c[5] * t3, t3, a[6]);
+      if (ORDER == 4) {
+        float c[4];
+        moment_terms4(g == 2, s, u, c);
+        a[1] = fmaf(c[0], t, a[1]);
+        a[2] = fmaf(c[1], t2, a[2]);
+        a[3] = fmaf(c[2], t3, a[3]);
+        a[4] = fmaf(c[3] * t2, t2, a[4]);
+      } else {
+        float c[6];
+        moment_terms(g == 2, s, u, c);
+        a[1] = fmaf(c[0], t, a[1]);
+        a[2] = fmaf(c[1], t2, a[2]);
+        a[3] = fmaf(c[2], t3, a[3]);
+        a[4] = fmaf(c[3] * t2, t2, a[4]);
+        a[5] = fmaf(c[4] * t2, t3, a[5]);
+        a[6] = fmaf(c[5] * t3, t3, a[6]);
+      }
       if (ok) qm[g] = fmaxf(qm[g], fabsf(qv));
     }
     if ((jj & 7) == 0) {
@@ -831,7 +841,10 @@ gate_gemm_tc_persistent(const GateGemmArgs p, const __grid_constant__ TcMaps map
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * C::NCOL + ((uint32_t)(quarter * 32) << 16);
-      if (MODE == GG_MOMENTS) epilogue_moments(p, t_row, ugrp, quarter, lane, n < p.n, qm, macc, pacc, sring, sfull_bar, sempty_bar, sit);
+      if (MODE == GG_MOMENTS) {
+        if (p.mom_order == 4) epilogue_moments<4>(p, t_row, ugrp, quarter, lane, n < p.n, qm, macc, pacc, sring, sfull_bar, sempty_bar, sit);
+        else epilogue_moments<6>(p, t_row, ugrp, quarter, lane, n < p.n, qm, macc, pacc, sring, sfull_bar, sempty_bar, sit);
+      }
       else if (STAGED) epilogue_staged<MODE>(p, t_row, ugrp, quarter, lane, j0, n, n < p.n, tl, msum, sring, sfull_bar, sempty_bar, sit);
       else epilogue_units<MODE>(p, t_row, ugrp * (JC / 4), (ugrp + 1) * (JC / 4), j0, n, n < p.n, tl, msum);
       tc_fence_before();

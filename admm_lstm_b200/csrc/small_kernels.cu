@@ -339,7 +339,8 @@ __global__ void weight_select_kernel(const double* est_acc, const double* fk_acc
     // f(w + G/2^k) = F0 + B1 x + ... + B6 x^6, x = 2^-k, valid where max|Q| x <= 2^-4 (admm_probe_plan).  kv = first
     // exponent at which it is; every k < kv must be covered by a lower bound that proves the loop continues past it.
     int kv = k0;
-    while (kv < ADMM_EST_CAND && !(ldexpf(qmax[g], -kv) <= 0.0625f)) ++kv;
+    const float valid = (plan.order == 4) ? 0.015625f : 0.0625f;       // |Q| 2^-k <= 2^-6 (order 4) / 2^-4 (order 6)
+    while (kv < ADMM_EST_CAND && !(ldexpf(qmax[g], -kv) <= valid)) ++kv;
     const int kp = plan.proof ? k0 + plan.ncand : 0;
     if (kv > kp && kv > 0) {
       done[4 + g] = 3; done[8 + g] = kv;             // expansion not valid where the bounds end: exact passes follow

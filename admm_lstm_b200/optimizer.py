@@ -130,6 +130,7 @@ class ADMMBasedOptimizer(object):
         log_assert(not (with_dual_y and variant == "no_dual_y"), "with_dual_y needs variant='admm'.")
         self.variant, self.with_dual_y = variant, bool(with_dual_y)
         self.probe = probe or os.environ.get("ADMM_LSTM_PROBE", "moments")
+        self.moment_order = int(os.environ.get("ADMM_LSTM_MOMENT_ORDER", "4"))      # 4 (fused pass) or 6; A/B switch
         log_assert(self.probe in ("moments", "exact"), f"probe must be 'moments' or 'exact' (Got: {self.probe}).")
         log_assert(sharding in ("slice", "presharded"), f"sharding must be 'slice' or 'presharded' (Got: {sharding}).")
         self.verbose = verbose
@@ -499,20 +500,24 @@ class ADMMBasedOptimizer(object):
             span = max(k + 3 - a for k, a in zip(ks, k0))
             ncand = min(_lib.ADMM_MAX_CAND, max(8, -(-span // 8) * 8))
             return [(tuple(k0), ncand, int(any(k0)), 0)] + full
+        # fused moment pass (tensor-core path with a z store): 4th-order expansion, valid two exponents later (|Q| 2^-k <= 2^-6)
+        # but a quarter fewer instructions per element in a kernel that is bound by them; otherwise 6th order (<= 2^-4)
+        order = 4 if (self.uses_tensor_cores and self._zstore is not None and self.moment_order != 6) else 6
+        lim = 2.0 ** -7 if order == 4 else 2.0 ** -5                  # a factor 2 inside the validity limit
         k0 = [0, 0, 0, 0]
         if self._hint_q is not None:
             for g, q in enumerate(self._hint_q[src]):
-                if q == q and q > 2.0 ** -5:                      # NaN-safe
-                    if not math.isfinite(q) or q >= 2.0 ** (_lib.ADMM_MAX_CAND - 7):
+                if q == q and q > lim:                            # NaN-safe
+                    if not math.isfinite(q) or q >= 2.0 ** (_lib.ADMM_MAX_CAND - 9):
                         return full          # a diverging run: the expansion's window would not fit, go straight to the exact passes
-                    k0[g] = int(math.ceil(math.log2(q * 32.0)))    # <= ADMM_MAX_CAND - 2, so the proofs (k0 + 2) fit
+                    k0[g] = int(math.ceil(math.log2(q / lim)))     # <= ADMM_MAX_CAND - 2, so the proofs (k0 + 2) fit
         if self.use_cuda_graph:
             # the plan is baked into a captured graph: one common, even k0 for the four gates changes rarely (a larger k0 is
             # always valid, it only moves candidates from the expansion to the lower-bound proofs)
             k0 = [min(_lib.ADMM_MAX_CAND - 2, (max(k0) + 1) // 2 * 2)] * 4
         # proofs always cover two exponents more than the hint asks for (ncand = 2): max|Q| may grow by 8x between the
         # hint and this step before the exact passes are needed
-        return [(tuple(k0), 2, 1, 1)] + full
+        return [(tuple(k0), 2, 1, 1, order)] + full
 
     def _push_theta_hint(self) -> None:
         slot = self._theta_ring[self._step_index % len(self._theta_ring)]
@@ -612,11 +617,13 @@ class ADMMBasedOptimizer(object):
         self._done.zero_()
         theta_ptr = self._theta_w[4 * src:].data_ptr()
         plans = self._probe_plans(src)
-        for q, (k0, ncand, proof, moments) in enumerate(plans):
+        for q, entry in enumerate(plans):
+            k0, ncand, proof, moments = entry[:4]
             plan = _lib.ProbePlan()
             for g in range(4):
                 plan.k0[g] = k0[g]
             plan.ncand, plan.proof, plan.moments = ncand, proof, moments
+            plan.order = entry[4] if len(entry) > 4 else 0
             self._acc_fk.zero_()
             if moments:
                 self._qmax.zero_()

@@ -78,7 +78,10 @@ typedef struct admm_probe_plan {
   int32_t ncand;
   int32_t proof;
   int32_t moments;
-  int32_t reserved_;
+  /* moments plans: order of the expansion, 6 (0 means 6) or 4.  Order 4 drops the delta^5 and delta^6 terms -- a quarter fewer
+   * instructions per element in the kernel that is bound by them -- and is used where max|Q| 2^-k <= 2^-6 (instead of 2^-4)
+   * keeps the truncated terms below 1e-10 per element; k0 is then two exponents larger. */
+  int32_t order;
 } admm_probe_plan;
 
 /* One rank's shard of the problem.  The optimizer owns every buffer (allocated by the host

@@ -288,8 +288,7 @@ class ADMMLOptimizer(object):
         for s in range(1, T + 1):
             rm, rs = cur[s], self._red_sum[s:s + 1]
             self._call("admm_l_sweep_gates", lpp, s, sp, rm.data_ptr(), rs.data_ptr(), st)
-            self.comm.allreduce_max_(rm[4:5])
-            self.comm.allreduce_sum_(rs)
+            self.comm.allreduce_max_and_sum_(rm[4:5], rs)      # one collective per timestep (MAX and SUM scalar together)
             self._call("admm_l_sweep_cell", lpp, s, sp, rm.data_ptr(), rs.data_ptr(), nxt[s].data_ptr(), st)
         self._call("admm_l_last", lpp, self._theta_h.data_ptr(), self._tmp.data_ptr(), sp, nxt[T].data_ptr(), st)
         self._red_cur = 1 - self._red_cur

@@ -43,6 +43,24 @@ class Comm:
         for t in tensors:
             self._reduce(t, dist.ReduceOp.MAX)
 
+    def allreduce_max_and_sum_(self, max_t: torch.Tensor, sum_t: torch.Tensor) -> None:
+        """One collective for a MAX-reduced and a SUM-reduced scalar (ADMM-LSTM-L needs both between the two kernels of every
+        timestep, admm_lstm.py:225,230): all-gather the pair, reduce locally in rank order -- identical on every rank."""
+        if not self.active:
+            return
+        pair = torch.stack([max_t.reshape(()).double(), sum_t.reshape(()).double()])
+        out = torch.empty((self.world_size, 2), dtype=torch.float64, device=pair.device)
+        if self.events is not None and pair.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_gather(list(out.unbind(0)), pair, group=self.group)
+            e1.record()
+            self.events.append((16, e0, e1))
+        else:
+            dist.all_gather(list(out.unbind(0)), pair, group=self.group)
+        max_t.copy_(out[:, 0].max().to(max_t.dtype).reshape(max_t.shape))
+        sum_t.copy_(out[:, 1].sum().to(sum_t.dtype).reshape(sum_t.shape))
+
     def enable_timing(self, enabled: bool = True) -> None:
         """Bracket every collective with CUDA events on the launching stream: the elapsed time of a collective is its
         transfer plus the wait for the slowest rank to arrive -- the evidence for what limits multi-GPU scaling."""

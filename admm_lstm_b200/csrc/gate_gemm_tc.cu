@@ -573,6 +573,19 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
   const float acc_scale = *p.acc_scale;
   const uint32_t my = (uint32_t)(ugrp * BM + quarter * 32 + lane);
   const float rho_g[4] = {p.rho.i, p.rho.f, p.rho.g, p.rho.o};
+  // per-gate constants of the tile, hoisted (the kernel is bound by its instruction count): lambda / rho as a multiplication
+  // when rho is a power of two (exact), as an IEEE division otherwise; Q -> t = Q 2^-k0 with the accumulator scale and the
+  // ghost-row mask folded in
+  float inv_rho[4], qscale[4], tscale[4];
+  bool rho_p2[4];
+  const float okf = ok ? 1.0f : 0.0f;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    rho_p2[g] = (__float_as_uint(rho_g[g]) & 0x007FFFFFu) == 0u;
+    inv_rho[g] = 1.0f / rho_g[g];
+    qscale[g] = acc_scale * okf;                                             // ghost rows: Q = 0 (no moment terms, no max)
+    tscale[g] = __int_as_float((127 - p.mom_k0[g]) << 23);                    // 2^-k0
+  }
   float acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
@@ -596,16 +609,14 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
     tmem_ld_wait();
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float rho = rho_g[g];
-      const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
-      const float lr = rho_pow2 ? lam[g] * (1.0f / rho) : __fdiv_rn(lam[g], rho);
-      const float qv = q[g] * acc_scale;
+      const float lr = rho_p2[g] ? lam[g] * inv_rho[g] : __fdiv_rn(lam[g], rho_g[g]);
+      const float qv = q[g] * qscale[g];
       const float s = (g == 2) ? FastMath::tanh(z0[g]) : FastMath::sigmoid(z0[g]);
       const float u = (s - lr) - gv[g];
-      const float t = ok ? qv * __int_as_float((127 - p.mom_k0[g]) << 23) : 0.f;       // Q 2^-k0; ghost rows contribute nothing
+      const float t = qv * tscale[g];                    // Q 2^-k0
       const float t2 = t * t, t3 = t2 * t;
       float* a = acc + g * 8;
-      a[0] = fmaf(ok ? u : 0.f, u, a[0]);
+      a[0] = fmaf(u * okf, u, a[0]);
       if (ORDER == 4) {
         float c[4];
         moment_terms4(g == 2, s, u, c);
@@ -623,7 +634,7 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
         a[5] = fmaf(c[4] * t2, t3, a[5]);
         a[6] = fmaf(c[5] * t3, t3, a[6]);
       }
-      if (ok) qm[g] = fmaxf(qm[g], fabsf(qv));
+      qm[g] = fmaxf(qm[g], fabsf(qv));
     }
     if ((jj & 7) == 0) {
       // Lower-bound proofs below the expansion (any subset sum of squares is a lower bound of f(beta_k)): the candidates
@@ -639,9 +650,7 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
         float v[32];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float rho = rho_g[g];
-          const bool rho_pow2 = (__float_as_uint(rho) & 0x007FFFFFu) == 0u;
-          const float lr = rho_pow2 ? lam[g] * (1.0f / rho) : __fdiv_rn(lam[g], rho);
+          const float lr = rho_p2[g] ? lam[g] * inv_rho[g] : __fdiv_rn(lam[g], rho_g[g]);
           const float qv = q[g] * acc_scale;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {

@@ -71,6 +71,12 @@ def _worker(rank, world, port, out_dir):
         m = torch.tensor([float(np.max(np.abs(o.h[0][lo:hi])))], dtype=torch.float64)
         comm.allreduce_max_(m)
         assert abs(float(m) - float(np.max(np.abs(o.h[0])))) < 1e-12
+        # the per-timestep pair of update_c (admm_lstm.py:225,230): one collective for the MAX and the SUM scalar
+        mx = torch.tensor([float(np.max(np.abs(o.c[0][lo:hi])))], dtype=torch.float32)
+        sm = torch.tensor([float(np.sum(np.square(o.h[0][lo:hi]), dtype=np.float64))], dtype=torch.float64)
+        comm.allreduce_max_and_sum_(mx, sm)
+        assert abs(float(mx) - float(np.max(np.abs(o.c[0])))) < 1e-6
+        assert abs(float(sm) - float(np.sum(np.square(o.h[0]), dtype=np.float64))) < 1e-9 * float(sm)
         wx = torch.stack([torch.from_numpy(o.W[g].copy()) for g in ORDER])
         wh = torch.stack([torch.from_numpy(o.U[g].copy()) for g in ORDER])
         wy = torch.from_numpy(o.Wy.copy()).reshape(-1)

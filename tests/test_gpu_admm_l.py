@@ -166,6 +166,10 @@ def test_l_sharded_fake_world_equals_single(shape, tc):
             for t in tensors:
                 self._reduce(t, torch.maximum)
 
+        def allreduce_max_and_sum_(self, max_t, sum_t):
+            self._reduce(max_t, torch.maximum)
+            self._reduce(sum_t, torch.add)
+
         def shard_range(self, n_total):
             half = (n_total + 1) // 2
             return (0, half) if self.rank == 0 else (half, n_total)

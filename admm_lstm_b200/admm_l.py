@@ -32,6 +32,9 @@ from .comm import Comm
 from .logging_utils import info
 from .optimizer import _feature_major, _require_cuda, _round_up, _stream_ptr
 
+# One all-gather of the (MAX, SUM) pair per timestep instead of two all-reduces: measured SLOWER (2 GPUs, cfg4 shape: 144.3
+# vs 141.3 ms per iteration -- the local reduction's extra small launches cost more than the saved collective), so off.
+_PAIR_COLLECTIVE = os.environ.get("ADMM_L_PAIR_COLLECTIVE", "0") != "0"
 _ORDER = ("i", "f", "g", "o")          # storage order of the stacked weights / state (as the main path)
 _UPDATE_ORDER = ("g", "o", "i", "f")   # main.py:141-148
 
@@ -288,7 +291,11 @@ class ADMMLOptimizer(object):
         for s in range(1, T + 1):
             rm, rs = cur[s], self._red_sum[s:s + 1]
             self._call("admm_l_sweep_gates", lpp, s, sp, rm.data_ptr(), rs.data_ptr(), st)
-            self.comm.allreduce_max_and_sum_(rm[4:5], rs)      # one collective per timestep (MAX and SUM scalar together)
+            if _PAIR_COLLECTIVE:
+                self.comm.allreduce_max_and_sum_(rm[4:5], rs)      # one collective per timestep (MAX and SUM scalar together)
+            else:
+                self.comm.allreduce_max_(rm[4:5])
+                self.comm.allreduce_sum_(rs)
             self._call("admm_l_sweep_cell", lpp, s, sp, rm.data_ptr(), rs.data_ptr(), nxt[s].data_ptr(), st)
         self._call("admm_l_last", lpp, self._theta_h.data_ptr(), self._tmp.data_ptr(), sp, nxt[T].data_ptr(), st)
         self._red_cur = 1 - self._red_cur

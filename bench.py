@@ -585,15 +585,19 @@ def main():
     lib = _lib.load()
 
     x, y, w = make_data(n_gpu, T, D, H, O, 1000 + rank, cls)
-    model = LSTM(D, H, O)
-    with torch.no_grad():
-        for k, v in w.items():
-            getattr(model, k).copy_(torch.from_numpy(v))
     x_pin = torch.from_numpy(x).pin_memory()
     y_pin = torch.from_numpy(y).pin_memory()
     params = bench_params(pname, n_gpu * max(world, 1), H)
-    opt = ADMMBasedOptimizer(model, (x_pin, y_pin), params, verbose=False, variant=args.variant,
-                             sharding="presharded", use_tensor_cores=(False if args.no_tc else None))
+
+    def build_opt():
+        model = LSTM(D, H, O)
+        with torch.no_grad():
+            for k, v in w.items():
+                getattr(model, k).copy_(torch.from_numpy(v))
+        return ADMMBasedOptimizer(model, (x_pin, y_pin), params, verbose=False, variant=args.variant,
+                                  sharding="presharded", use_tensor_cores=(False if args.no_tc else None))
+
+    opt = build_opt()
     del x, y
     n_total = opt.n_global
 
@@ -675,7 +679,19 @@ def main():
               "wy": torch.empty((H, O)).pin_memory(), "metrics": torch.empty(_lib.ADMM_N_METRICS, dtype=torch.float64).pin_memory()}
     h2d = x_pin.numel() * 4 + y_pin.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in pinned.values())
-    # one untimed end-to-end iteration first: it allocates the staging buffers and the copy stream
+    # The end-to-end region runs the SAME iterations as the device-resident one: a fresh optimizer, the same W warm-up steps
+    # (the last of them end to end: it allocates the staging buffers and the copy stream), then K timed steps.  The iteration
+    # itself drifts on these synthetic workloads (max|Q| of the probes grows ~1.5x per 5 iterations; from iteration ~45 of cfg3
+    # on the lower-bound proofs stop being conclusive and the exact passes run: scripts/long_run.py,
+    # profiles/r02_ag_long_run_cfg3.txt), so the two regions must not sit at different iteration indices.
+    graphs_first = (opt.graph_replays, len(opt._graphs))
+    del opt
+    import gc
+    gc.collect()                      # the state views hold reference cycles: free the 140 GB before allocating them again
+    torch.cuda.empty_cache()
+    opt = build_opt()
+    for _ in range(max(args.warmup, 3) - 1):
+        opt.step()
     opt.prefetch_inputs(x_pin, y_pin)
     opt.refresh_inputs()
     opt.step()
@@ -758,7 +774,7 @@ def main():
             "e2e": {"value": n_total * T / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "per_step_ms": e2e_per_step},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "comm": comm_info,
-            "cuda_graph": {"replays": opt.graph_replays, "graphs": len(opt._graphs)},
+            "cuda_graph": {"replays": graphs_first[0], "graphs": graphs_first[1]},
             "tensor_cores": bool(opt.uses_tensor_cores),
             "step_tflops_useful": step_flops / (ms_step * 1e-3) / 1e12,
             "kernel_ms_per_step": {k: round(v[1] / ksteps, 3) for k, v in sorted(ksum.items(), key=lambda kv: -kv[1][1])},

@@ -749,6 +749,9 @@ def test_reinstalled_inputs_keep_or_drop_the_stored_preactivations():
     x2t, y2t = torch.from_numpy(x2), torch.from_numpy(y2)
     a.refresh_inputs(x2t, y2t)
     c.refresh_inputs(x2t, y2t)
+    # the transposing install itself: device layout [T][D][ldn] / [O][ldn], ghost columns untouched (zero)
+    assert torch.equal(a._x[:, :, :n].cpu(), x2t.permute(1, 2, 0)) and torch.equal(a._y[:, :n].cpu(), y2t.t())
+    assert float(a._x[:, :, n:].abs().max()) == 0.0 and float(a._y[:, n:].abs().max()) == 0.0
     for _ in range(2):
         a.step()
         c.step()

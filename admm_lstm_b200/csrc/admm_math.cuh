@@ -125,6 +125,34 @@ __device__ __forceinline__ void moment_terms4(bool is_g, float s, float u, float
 }
 #endif
 
+#if defined(__CUDACC__)
+// moment_terms4 and its accumulation in one: a[k] += c_k t^k, k = 1..4, with the common factor D1 = act'(z) taken into the
+// powers (w_k = D1 t^k) and the brackets of c_k / D1 written out -- 21 (tanh) / 23 (sigmoid) instructions instead of 33:
+//   sigmoid (m = 1 - 2 s):  c1 = D1 2u,  c2 = D1 (D1 + u m),  c3 = D1 (D1 m + u (1/3 - 2 D1)),
+//                           c4 = D1 (D1 (m^2 / 4 + 1/3 - 2 D1) + u m (1/12 - D1))
+//   tanh (e = 1/3 - s^2):   c1 = D1 2u,  c2 = D1 (D1 - 2u s),  c3 = D1 (-2 s D1 - 2u e),
+//                           c4 = D1 (D1 (s^2 - 2 e) + 2u s (2/3 - s^2))
+// (the same polynomials as moment_terms4, checked term by term in float64 and for bias in fp32 sums).
+__device__ __forceinline__ void moment_accum4(bool is_g, float s, float u, float t, float* a) {
+  const float u2 = u + u;
+  if (is_g) {
+    const float s2 = s * s, d1 = 1.0f - s2, e = (1.0f / 3.0f) - s2, us = u2 * s;
+    const float w1 = d1 * t, w2 = w1 * t, w3 = w2 * t, w4 = w3 * t;
+    a[1] = fmaf(w1, u2, a[1]);
+    a[2] = fmaf(w2, d1 - us, a[2]);
+    a[3] = fmaf(w3, fmaf(-2.0f, s * d1, -(u2 * e)), a[3]);
+    a[4] = fmaf(w4, fmaf(d1, fmaf(-2.0f, e, s2), us * ((2.0f / 3.0f) - s2)), a[4]);
+  } else {
+    const float d1 = s * (1.0f - s), m = fmaf(-2.0f, s, 1.0f), e = fmaf(-2.0f, d1, 1.0f / 3.0f), um = u * m;
+    const float w1 = d1 * t, w2 = w1 * t, w3 = w2 * t, w4 = w3 * t;
+    a[1] = fmaf(w1, u2, a[1]);
+    a[2] = fmaf(w2, d1 + um, a[2]);
+    a[3] = fmaf(w3, fmaf(u, e, d1 * m), a[3]);
+    a[4] = fmaf(w4, fmaf(d1, fmaf(0.25f, m * m, e), um * ((1.0f / 12.0f) - d1)), a[4]);
+  }
+}
+#endif
+
 // admm.py:239-244, expressed through the activation value itself
 ADMM_HD float dsigmoid_from(float s) { return s * (1.0f - s); }
 ADMM_HD float dtanh_from(float t) { return 1.0f - t * t; }

@@ -558,6 +558,14 @@ __device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
   }
 }
 
+// a / b correctly rounded from y = RN(1 / b) (Markstein: q = RN(a y), r = a - b q exactly by FMA, RN(q + r y) is the
+// correctly rounded quotient): the value __fdiv_rn returns for every normal-range operand, in three instructions instead of
+// the ten of the general division (reciprocal refinement, FCHK, slow-path branch) -- the reference divides (admm.py:318).
+__device__ __forceinline__ float div_rn(float a, float b, float y) {
+  const float q = a * y;
+  return fmaf(fmaf(-b, q, a), y, q);
+}
+
 // exact residual of one candidate: the activations of probe_eval.cu (two MUFU ops, <= 2 ulp)
 __device__ __forceinline__ float moments_exact_u(bool is_g, float z, float lr, float gv) {
   const float a = is_g ? FastMath::tanh(z) : FastMath::sigmoid(z);
@@ -573,16 +581,14 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
   const float acc_scale = *p.acc_scale;
   const uint32_t my = (uint32_t)(ugrp * BM + quarter * 32 + lane);
   const float rho_g[4] = {p.rho.i, p.rho.f, p.rho.g, p.rho.o};
-  // per-gate constants of the tile, hoisted (the kernel is bound by its instruction count): lambda / rho as a multiplication
-  // when rho is a power of two (exact), as an IEEE division otherwise; Q -> t = Q 2^-k0 with the accumulator scale and the
-  // ghost-row mask folded in
+  // per-gate constants of the tile, hoisted (the kernel is bound by its instruction count): lambda / rho is the correctly
+  // rounded quotient in three instructions (div_rn below) from the correctly rounded reciprocal; Q -> t = Q 2^-k0 with the
+  // accumulator scale and the ghost-row mask folded in
   float inv_rho[4], qscale[4], tscale[4];
-  bool rho_p2[4];
   const float okf = ok ? 1.0f : 0.0f;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    rho_p2[g] = (__float_as_uint(rho_g[g]) & 0x007FFFFFu) == 0u;
-    inv_rho[g] = 1.0f / rho_g[g];
+    inv_rho[g] = __fdiv_rn(1.0f, rho_g[g]);
     qscale[g] = acc_scale * okf;                                             // ghost rows: Q = 0 (no moment terms, no max)
     tscale[g] = __int_as_float((127 - p.mom_k0[g]) << 23);                    // 2^-k0
   }
@@ -609,22 +615,17 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
     tmem_ld_wait();
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float lr = rho_p2[g] ? lam[g] * inv_rho[g] : __fdiv_rn(lam[g], rho_g[g]);
+      const float lr = div_rn(lam[g], rho_g[g], inv_rho[g]);
       const float qv = q[g] * qscale[g];
       const float s = (g == 2) ? FastMath::tanh(z0[g]) : FastMath::sigmoid(z0[g]);
       const float u = (s - lr) - gv[g];
       const float t = qv * tscale[g];                    // Q 2^-k0
-      const float t2 = t * t, t3 = t2 * t;
       float* a = acc + g * 8;
       a[0] = fmaf(u * okf, u, a[0]);
       if (ORDER == 4) {
-        float c[4];
-        moment_terms4(g == 2, s, u, c);
-        a[1] = fmaf(c[0], t, a[1]);
-        a[2] = fmaf(c[1], t2, a[2]);
-        a[3] = fmaf(c[2], t3, a[3]);
-        a[4] = fmaf(c[3] * t2, t2, a[4]);
+        moment_accum4(g == 2, s, u, t, a);
       } else {
+        const float t2 = t * t, t3 = t2 * t;
         float c[6];
         moment_terms(g == 2, s, u, c);
         a[1] = fmaf(c[0], t, a[1]);
@@ -650,7 +651,7 @@ __device__ __forceinline__ void epilogue_moments(const GateGemmArgs& p, uint32_t
         float v[32];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float lr = rho_p2[g] ? lam[g] * inv_rho[g] : __fdiv_rn(lam[g], rho_g[g]);
+          const float lr = div_rn(lam[g], rho_g[g], inv_rho[g]);
           const float qv = q[g] * acc_scale;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
@@ -1609,6 +1610,7 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(atr_tc_kernel<NT_, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(atr_tc_kernel<NT_, F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   AtrMaps m;
@@ -1632,8 +1634,12 @@ int launch_atr(const admm_problem* p, const AtrArgs& a, int slab0, bool src_is_x
   if (rc) return ADMM_ECUDA;
   const int n_chunks = (int)(tc * (ldn / BKN));
   const int tiles = (int)((rows / 128) * ((a.K + NT_ - 1) / NT_));
-  int splits = (148 + tiles - 1) / tiles;
-  if (tiles * splits > 148 && splits > 1) --splits;          // stay within one wave of 148 single-CTA SMs
+  // one wave: 148 SMs x the CTAs that fit next to each other (NT = 64: two 97 KB rings per SM -- the K = D pass is bound by
+  // HBM, and 32 tiles x 4 splits left 20 SMs without a CTA and 96 KB per SM in flight)
+  constexpr int CTAS_PER_SM = (2 * SMEM <= 227 * 1024) ? 2 : 1;
+  constexpr int WAVE = 148 * CTAS_PER_SM;
+  int splits = (WAVE + tiles - 1) / tiles;
+  if (tiles * splits > WAVE && splits > 1) --splits;
   splits = max(1, min(splits, n_chunks));
   const int cpc = (n_chunks + splits - 1) / splits;
   splits = (n_chunks + cpc - 1) / cpc;

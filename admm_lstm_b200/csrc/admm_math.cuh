@@ -20,6 +20,16 @@ struct Rho { float i, f, g, o, c, h, y; };
 ADMM_HD float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }     // admm.py:235-237
 ADMM_HD float tanh_f(float x) { return tanhf(x); }                         // admm.py:231-233
 
+// a / b correctly rounded from y = RN(1 / b) (Markstein: q = RN(a y), r = a - b q exactly by FMA, RN(q + r y) is the
+// correctly rounded quotient): the value an IEEE division returns for every normal-range operand, in three instructions
+// instead of the ten of the general division (reciprocal refinement, FCHK, slow-path branch).  Used where the reference
+// divides by a per-gate constant (lambda / rho, admm.py:318) inside an instruction-bound epilogue; tests/test_cabi_and_host.py
+// compares it bit for bit with the host's division.
+ADMM_HD float div_rn(float a, float b, float y) {
+  const float q = a * y;
+  return fmaf(fmaf(-b, q, a), y, q);
+}
+
 // Math policies of the per-element closed forms.  Accurate = libm-class functions and IEEE division (the CUDA-core
 // path, the host build, everything the knife-edge parity tests look at).  Fast (device only) = two MUFU ops per
 // activation (ex2.approx + rcp.approx with one Newton step; degree-5 odd polynomial for |x| < 0.6 in tanh) and
@@ -100,9 +110,8 @@ __device__ __forceinline__ void moment_terms(bool is_g, float s, float u, float 
 }
 #endif
 
-#if defined(__CUDACC__)
 // The same up to 4th order (c1..c4): valid for |d| <= 2^-6 at the accuracy moment_terms has for |d| <= 2^-4.
-__device__ __forceinline__ void moment_terms4(bool is_g, float s, float u, float (&c)[4]) {
+ADMM_HD void moment_terms4(bool is_g, float s, float u, float (&c)[4]) {
   float a1, a2, a3, a4;
   if (is_g) {
     const float t2 = s * s, d1 = 1.0f - t2;
@@ -123,9 +132,7 @@ __device__ __forceinline__ void moment_terms4(bool is_g, float s, float u, float
   c[2] = fmaf(u2, a3, 2.0f * a1 * a2);
   c[3] = fmaf(u2, a4, fmaf(2.0f * a1, a3, a2 * a2));
 }
-#endif
 
-#if defined(__CUDACC__)
 // moment_terms4 and its accumulation in one: a[k] += c_k t^k, k = 1..4, with the common factor D1 = act'(z) taken into the
 // powers (w_k = D1 t^k) and the brackets of c_k / D1 written out -- 21 (tanh) / 23 (sigmoid) instructions instead of 33:
 //   sigmoid (m = 1 - 2 s):  c1 = D1 2u,  c2 = D1 (D1 + u m),  c3 = D1 (D1 m + u (1/3 - 2 D1)),
@@ -133,7 +140,7 @@ __device__ __forceinline__ void moment_terms4(bool is_g, float s, float u, float
 //   tanh (e = 1/3 - s^2):   c1 = D1 2u,  c2 = D1 (D1 - 2u s),  c3 = D1 (-2 s D1 - 2u e),
 //                           c4 = D1 (D1 (s^2 - 2 e) + 2u s (2/3 - s^2))
 // (the same polynomials as moment_terms4, checked term by term in float64 and for bias in fp32 sums).
-__device__ __forceinline__ void moment_accum4(bool is_g, float s, float u, float t, float* a) {
+ADMM_HD void moment_accum4(bool is_g, float s, float u, float t, float* a) {
   const float u2 = u + u;
   if (is_g) {
     const float s2 = s * s, d1 = 1.0f - s2, e = (1.0f / 3.0f) - s2, us = u2 * s;
@@ -151,7 +158,6 @@ __device__ __forceinline__ void moment_accum4(bool is_g, float s, float u, float
     a[4] = fmaf(w4, fmaf(d1, fmaf(0.25f, m * m, e), um * ((1.0f / 12.0f) - d1)), a[4]);
   }
 }
-#endif
 
 // admm.py:239-244, expressed through the activation value itself
 ADMM_HD float dsigmoid_from(float s) { return s * (1.0f - s); }

@@ -558,14 +558,6 @@ __device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
   }
 }
 
-// a / b correctly rounded from y = RN(1 / b) (Markstein: q = RN(a y), r = a - b q exactly by FMA, RN(q + r y) is the
-// correctly rounded quotient): the value __fdiv_rn returns for every normal-range operand, in three instructions instead of
-// the ten of the general division (reciprocal refinement, FCHK, slow-path branch) -- the reference divides (admm.py:318).
-__device__ __forceinline__ float div_rn(float a, float b, float y) {
-  const float q = a * y;
-  return fmaf(fmaf(-b, q, a), y, q);
-}
-
 // exact residual of one candidate: the activations of probe_eval.cu (two MUFU ops, <= 2 ulp)
 __device__ __forceinline__ float moments_exact_u(bool is_g, float z, float lr, float gv) {
   const float a = is_g ? FastMath::tanh(z) : FastMath::sigmoid(z);

@@ -27,6 +27,32 @@ void admm_host_grad_points(const float* z, const float* lam, const float* gate, 
   for (long e = 0; e < n; ++e) R[e] = admm::grad_point(z[e], lam[e], gate[e], rho, is_g != 0, &u[e]);
 }
 
+// lambda / rho the way the fused moment pass forms it (div_rn from the correctly rounded reciprocal)
+void admm_host_div_rn(const float* a, float b, float* out, long n) {
+  const float y = 1.0f / b;
+  for (long e = 0; e < n; ++e) out[e] = admm::div_rn(a[e], b, y);
+}
+
+// sums over the elements of c_k t^k, k = 1..4 (double accumulation of the fp32 terms): [0..3] from moment_terms4 (coefficients,
+// then powers), [4..7] from moment_accum4 (the fused form the epilogue runs); s = act(z) is formed here in double precision
+void admm_host_moment_sums4(const float* z, const float* c, const float* t, int is_g, double* out, long n) {
+  for (int k = 0; k < 8; ++k) out[k] = 0.0;
+  for (long e = 0; e < n; ++e) {
+    const float s = is_g ? (float)tanh((double)z[e]) : (float)(1.0 / (1.0 + exp(-(double)z[e])));
+    const float u = s - c[e];
+    float co[4];
+    admm::moment_terms4(is_g != 0, s, u, co);
+    const float t1 = t[e], t2 = t1 * t1, t3 = t2 * t1;
+    out[0] += (double)(co[0] * t1);
+    out[1] += (double)(co[1] * t2);
+    out[2] += (double)(co[2] * t3);
+    out[3] += (double)((co[3] * t2) * t2);
+    float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    admm::moment_accum4(is_g != 0, s, u, t1, a);
+    for (int k = 0; k < 4; ++k) out[4 + k] += (double)a[1 + k];
+  }
+}
+
 void admm_host_probe_points(const float* z0, const float* q, float inv_theta, const float* lam, const float* gate,
                             float rho, int is_g, float* out, long n) {
   for (long e = 0; e < n; ++e)

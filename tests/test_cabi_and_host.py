@@ -200,3 +200,58 @@ def test_lstm_forward_matches_oracle():
         np.testing.assert_allclose(mine[k].numpy(), st[k], rtol=1e-5, atol=1e-6)
     m.with_grad = True
     np.testing.assert_allclose(m(x).detach().numpy(), st["a"], rtol=1e-5, atol=1e-6)
+
+
+def test_three_instruction_division_is_the_ieee_quotient():
+    """csrc/admm_math.cuh div_rn (lambda / rho in the fused moment pass) == the host's IEEE division, bit for bit, for the
+    rho of every shipped parameter set and a sweep of magnitudes of lambda down to the subnormal results (admm.py:318 divides)."""
+    _, host = _build()
+    lib = ctypes.CDLL(host)
+    fp = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(7)
+    rhos = {float(np.float32(v)) for params in (GOOGLE, HAR) for v in params["rho"].values()}
+    rhos |= {1.0, 0.5, 3.0, 1.0000001, 1.9999999, 5.62e-5, 7.77e-4} | set(rng.uniform(1e-6, 10.0, 16).tolist())
+    n = 200_000
+    lam = (rng.standard_normal(n) * 10.0 ** rng.uniform(-20, 3, n)).astype(np.float32)
+    lam[:4] = [0.0, -0.0, 1.0, -1.0]
+    out = np.empty(n, dtype=np.float32)
+    for rho in sorted(rhos):
+        lib.admm_host_div_rn(lam.ctypes.data_as(fp), ctypes.c_float(rho), out.ctypes.data_as(fp), ctypes.c_long(n))
+        want = lam / np.float32(rho)
+        nz = want != 0                                   # -0 / rho comes out as +0: the only difference, and not one in value
+        assert np.array_equal(out[nz].view(np.uint32), want[nz].view(np.uint32)) and not np.any(out[~nz]), \
+            (rho, int((out != want).sum()))
+
+
+@pytest.mark.parametrize("is_g", [0, 1])
+def test_fused_moment_accumulation_equals_coefficient_form(is_g):
+    """moment_accum4 (what the epilogue runs) == moment_terms4 followed by the powers of t (round 2's first form) to fp32
+    rounding of the individual terms, without bias in the sums: both against each other and against the float64 polynomial."""
+    _, host = _build()
+    lib = ctypes.CDLL(host)
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(11 + is_g)
+    n = 1_000_000
+    z = (rng.standard_normal(n) * 2.5).astype(np.float32)
+    c = (rng.standard_normal(n) * 0.3 + 0.4).astype(np.float32)
+    t = (rng.standard_normal(n) * 2.0 ** -8).clip(-2.0 ** -6, 2.0 ** -6).astype(np.float32)
+    out = np.zeros(8)
+    lib.admm_host_moment_sums4(z.ctypes.data_as(fp), c.ctypes.data_as(fp), t.ctypes.data_as(fp), ctypes.c_int(is_g),
+                               out.ctypes.data_as(dp), ctypes.c_long(n))
+    # float64 polynomial from the same fp32 s, u, t
+    z64, t64 = z.astype(np.float64), t.astype(np.float64)
+    s = (np.tanh(z64) if is_g else 1.0 / (1.0 + np.exp(-z64))).astype(np.float32).astype(np.float64)
+    u = (s.astype(np.float32) - c).astype(np.float64)
+    if is_g:
+        d1 = 1 - s * s
+        a = [d1, -s * d1, -d1 * (1 - 3 * s * s) / 3, s * d1 * (2 - 3 * s * s) / 3]
+    else:
+        d1, m = s * (1 - s), 1 - 2 * s
+        a = [d1, d1 * m / 2, d1 * (1 - 6 * d1) / 6, d1 * m * (1 - 12 * d1) / 24]
+    co = [2 * u * a[0], a[0] ** 2 + 2 * u * a[1], 2 * a[0] * a[1] + 2 * u * a[2], a[1] ** 2 + 2 * a[0] * a[2] + 2 * u * a[3]]
+    for k in range(4):
+        terms = co[k] * t64 ** (k + 1)
+        exact, scale = terms.sum(), np.abs(terms).sum()
+        assert abs(out[k] - exact) <= 2e-7 * scale, (k, out[k], exact)           # first form
+        assert abs(out[4 + k] - exact) <= 2e-7 * scale, (k, out[4 + k], exact)   # fused form
+        assert abs(out[4 + k] - out[k]) <= 2e-7 * scale

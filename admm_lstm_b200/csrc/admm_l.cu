@@ -144,6 +144,7 @@ __device__ __forceinline__ int l_cap_exp(unsigned max_bits) {
 __global__ void __launch_bounds__(NT) l_pack_kernel(const LPack p) {
   const int64_t per_t = (int64_t)p.H * p.ldn;
   const float r_scale = p.r16_hi ? ldexpf(1.0f, l_cap_exp(*p.r_bound)) : 1.0f;
+  const float irho_s = 1.0f / p.rho_s;
   const int rows = p.H * p.tc;
   for (int row = blockIdx.y; row < rows; row += gridDim.y) {
     const int tl = row / p.H, j = row - tl * p.H;
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(NT) l_pack_kernel(const LPack p) {
       for (int g = 0; g < 4; ++g) {
         const float2 z = *reinterpret_cast<const float2*>(p.z[g] + so);
         const float2 l = *reinterpret_cast<const float2*>(p.lam_s[g] + so);
-        v[g].x = z.x + l.x / p.rho_s;
-        v[g].y = z.y + l.y / p.rho_s;
+        v[g].x = z.x + div_rn(l.x, p.rho_s, irho_s);
+        v[g].y = z.y + div_rn(l.y, p.rho_s, irho_s);
       }
       v[4] = *reinterpret_cast<const float2*>(p.h + sp);
       const bool ok0 = n < p.n, ok1 = n + 1 < p.n;
@@ -202,14 +203,29 @@ __global__ void __launch_bounds__(NT) l_pt_kernel(const float* hT, const float* 
 
 // ---------------------------------------------------------------------------------------------------- sweep
 // update_z / update_zg (admm_lstm.py:166-188)
-__device__ __forceinline__ float l_update_z(float z, float out, float P, float lam1, float lam2, float rs, float rp,
-                                            float appro, bool is_g) {
+// Every division by a kernel-uniform constant (rho_s, rho_p, rho9, rho10 and the denominators built from them) is
+// div_rn(a, b, 1 / b) (admm_math.cuh): the IEEE quotient in three instructions instead of ten -- these kernels execute
+// ~600 instructions per element, a third of them such divisions.
+struct LRcp {
+  float rs, rp, r9, r10;          // rho_s, rho_p, rho9, rho10
+  float irs, irp, ir9, ir10;      // their correctly rounded reciprocals
+  __device__ __forceinline__ explicit LRcp(const admm_l_hyper& hp)
+      : rs(hp.rho_s), rp(hp.rho_p), r9(hp.rho9), r10(hp.rho10), irs(1.0f / hp.rho_s), irp(1.0f / hp.rho_p), ir9(1.0f / hp.rho9),
+        ir10(1.0f / hp.rho10) {}
+};
+struct LZDen {                     // 2 rho_s + rho_p appro of update_z / update_zg and its reciprocal
+  float den, iden;
+  __device__ __forceinline__ LZDen(const LRcp& k, float appro) : den(2.0f * k.rs + k.rp * appro), iden(1.0f / (2.0f * k.rs + k.rp * appro)) {}
+};
+__device__ __forceinline__ float l_update_z(float z, float out, float P, float lam1, float lam2, const LRcp& k, float appro,
+                                            const LZDen& zd, bool is_g) {
+  const float rs = k.rs, rp = k.rp;
   const float act = is_g ? tanhf(z) : l_sig(z);
   const float der = is_g ? 1.0f - act * act : act * (1.0f - act);
-  const float form1 = P - lam1 / rs;
-  const float form2 = rp * (act - out + lam2 / rp) * der;
+  const float form1 = P - div_rn(lam1, rs, k.irs);
+  const float form2 = rp * (act - out + div_rn(lam2, rp, k.irp)) * der;
   const float form3 = rs * form1 + 0.5f * rp * appro * z - form2;
-  return 2.0f * form3 / (2.0f * rs + rp * appro);
+  return div_rn(2.0f * form3, zd.den, zd.iden);
 }
 
 // z_f,f, z_i,i, z_o,o, z_g,g (main.py:150-165) + the reductions update_c needs
@@ -217,9 +233,11 @@ __global__ void __launch_bounds__(NT) l_gates_kernel(const LSlot p, float* red_m
   __shared__ float red[NT / 32];
   __shared__ double redd[NT / 32];
   const int64_t total = (int64_t)p.H * p.ldn;
-  const float rs = p.hp.rho_s, rp = p.hp.rho_p, r9 = p.hp.rho9, r10 = p.hp.rho10;
+  const LRcp k(p.hp);
+  const float rp = k.rp, r9 = k.r9, r10 = k.r10;
   const float ap_i = appro_sig(red_max[0]), ap_f = appro_sig(red_max[1]), ap_g = appro_tanh(red_max[2]),
               ap_o = appro_sig(red_max[3]);
+  const LZDen zd_i(k, ap_i), zd_f(k, ap_f), zd_g(k, ap_g), zd_o(k, ap_o);
   float mx = 0.f, so2 = 0.f;
   for (int j = blockIdx.y; j < p.H; j += gridDim.y)
   for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
@@ -230,21 +248,22 @@ __global__ void __launch_bounds__(NT) l_gates_kernel(const LSlot p, float* red_m
     const float l9 = p.lam9[idx], l10 = p.lam10[idx];
     const float lpi = p.lam_p[0][idx], lpf = p.lam_p[1][idx], lpg = p.lam_p[2][idx], lpo = p.lam_p[3][idx];
     // f
-    const float zf = l_update_z(p.z[1][idx], f, Pf, p.lam_s[1][idx], lpf, rs, rp, ap_f, false);
-    f = (rp * (l_sig(zf) + lpf / rp) + r9 * c_ * (ct - g * i + l9 / r9)) / (rp + r9 * c_ * c_);          // :191-196
+    const float l9r = div_rn(l9, r9, k.ir9), l10r = div_rn(l10, r10, k.ir10);
+    const float zf = l_update_z(p.z[1][idx], f, Pf, p.lam_s[1][idx], lpf, k, ap_f, zd_f, false);
+    f = (rp * (l_sig(zf) + div_rn(lpf, rp, k.irp)) + r9 * c_ * (ct - g * i + l9r)) / (rp + r9 * c_ * c_);   // :191-196
     // i
-    const float zi = l_update_z(p.z[0][idx], i, Pi, p.lam_s[0][idx], lpi, rs, rp, ap_i, false);
-    i = (rp * (l_sig(zi) + lpi / rp) + r9 * g * (ct - c_ * f + l9 / r9)) / (rp + r9 * g * g);            // :199-204
+    const float zi = l_update_z(p.z[0][idx], i, Pi, p.lam_s[0][idx], lpi, k, ap_i, zd_i, false);
+    i = (rp * (l_sig(zi) + div_rn(lpi, rp, k.irp)) + r9 * g * (ct - c_ * f + l9r)) / (rp + r9 * g * g);     // :199-204
     // o
-    const float zo = l_update_z(p.z[3][idx], o, Po, p.lam_s[3][idx], lpo, rs, rp, ap_o, false);
+    const float zo = l_update_z(p.z[3][idx], o, Po, p.lam_s[3][idx], lpo, k, ap_o, zd_o, false);
     const float tc = tanhf(ct);
-    o = (rp * (l_sig(zo) + lpo / rp) + r10 * tc * (h - l10 / r10)) / (rp + r10 * tc * tc);               // :207-212
+    o = (rp * (l_sig(zo) + div_rn(lpo, rp, k.irp)) + r10 * tc * (h - l10r)) / (rp + r10 * tc * tc);         // :207-212
     // g
-    const float zg = l_update_z(p.z[2][idx], g, Pg, p.lam_s[2][idx], lpg, rs, rp, ap_g, true);
-    g = (rp * (tanhf(zg) + lpg / rp) + r9 * i * (ct - c_ * f + l9 / r9)) / (rp + r9 * i * i);            // :215-220
+    const float zg = l_update_z(p.z[2][idx], g, Pg, p.lam_s[2][idx], lpg, k, ap_g, zd_g, true);
+    g = (rp * (tanhf(zg) + div_rn(lpg, rp, k.irp)) + r9 * i * (ct - c_ * f + l9r)) / (rp + r9 * i * i);     // :215-220
     p.z[0][idx] = zi; p.z[1][idx] = zf; p.z[2][idx] = zg; p.z[3][idx] = zo;
     p.gate[0][idx] = i; p.gate[1][idx] = f; p.gate[2][idx] = g; p.gate[3][idx] = o;
-    mx = fmaxf(mx, fabsf((h - l10 / r10) * 1.0f / o));                                                  // :225
+    mx = fmaxf(mx, fabsf((h - l10r) * 1.0f / o));                                                       // :225
     so2 = fmaf(o, o, so2);                                                                              // :230
   }
   const float bm = block_max(mx, red);
@@ -276,8 +295,8 @@ __device__ __forceinline__ LDualIn l_duals_load(const LSlot& p, int64_t idx, int
   return d;
 }
 __device__ __forceinline__ void l_duals_store(const LSlot& p, int64_t idx, const LDualIn& d, float c, float h, float c_,
-                                              float (&acc)[5]) {     // acc[0..3]: next iteration's maxima, acc[4]: |V|, |h| bound
-  const float rs = p.hp.rho_s, rp = p.hp.rho_p, r9 = p.hp.rho9, r10 = p.hp.rho10;
+                                              float (&acc)[5], const LRcp& k) {   // acc[0..3]: next iteration's maxima, acc[4]: |V|, |h| bound
+  const float rs = k.rs, rp = k.rp, r9 = k.r9, r10 = k.r10;
   const float n10 = d.l10 + r10 * (tanhf(c) * d.o - h);
   const float n9 = d.l9 + r9 * (c - d.g * d.i - c_ * d.f);
   const float gv[4] = {d.i, d.f, d.g, d.o};
@@ -288,8 +307,8 @@ __device__ __forceinline__ void l_duals_store(const LSlot& p, int64_t idx, const
     const float act = (q == 2) ? tanhf(d.z[q]) : l_sig(d.z[q]);
     np_[q] = d.lp[q] + rp * (act - gv[q]);
     ns_[q] = d.ls[q] + rs * (d.z[q] - d.P[q]);
-    b = fmaxf(b, fabsf(d.z[q] + ns_[q] / rs));          // |V| of the next packing pass (l_pack_kernel)
-    acc[q] = fmaxf(acc[q], fabsf(gv[q] - np_[q] / rp));  // admm_lstm.py:168,179 of the next iteration
+    b = fmaxf(b, fabsf(d.z[q] + div_rn(ns_[q], rs, k.irs)));          // |V| of the next packing pass (l_pack_kernel)
+    acc[q] = fmaxf(acc[q], fabsf(gv[q] - div_rn(np_[q], rp, k.irp)));  // admm_lstm.py:168,179 of the next iteration
   }
   p.lam10[idx] = n10;
   p.lam9[idx] = n9;
@@ -302,9 +321,12 @@ __device__ __forceinline__ void l_duals_store(const LSlot& p, int64_t idx, const
 template <bool LAST>
 __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* red_max, const double* red_sum) {
   const int64_t total = (int64_t)p.H * p.ldn;
-  const float r9 = p.hp.rho9, r10 = p.hp.rho10;
+  const LRcp k(p.hp);
+  const float r9 = k.r9, r10 = k.r10;
   const float appro_h = appro_tanh(red_max[4]);
   const float qua_o = (float)red_sum[0];
+  const float form4 = r9 + 0.5f * r10 * qua_o * appro_h;         // uniform: the same for every element of the timestep
+  const float iform4 = 1.0f / form4;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int j = blockIdx.y; j < p.H; j += gridDim.y)
   for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
@@ -312,20 +334,20 @@ __global__ void __launch_bounds__(NT) l_cell_kernel(const LSlot p, const float* 
     const LDualIn d = l_duals_load(p, idx, total);
     const float i = d.i, f = d.f, g = d.g, o = d.o, l9 = d.l9, l10 = d.l10;
     const float ct = p.gate[4][idx], h = p.gate[5][idx], c_ = p.c_prev[idx];
-    const float form1 = r9 * (g * i + c_ * f - l9 / r9);
+    const float l10r = div_rn(l10, r10, k.ir10);
+    const float form1 = r9 * (g * i + c_ * f - div_rn(l9, r9, k.ir9));
     const float tc = tanhf(ct);
-    const float form2 = r10 * (tc * o - h + l10 / r10) * (1.0f - tc * tc) * o;
+    const float form2 = r10 * (tc * o - h + l10r) * (1.0f - tc * tc) * o;
     const float form3 = 0.5f * r10 * qua_o * ct * appro_h;
-    const float form4 = r9 + 0.5f * r10 * qua_o * appro_h;
-    const float c = (form1 - form2 + form3) / form4;
+    const float c = div_rn(form1 - form2 + form3, form4, iform4);
     if (LAST) {
       p.gate[4][idx] = c;
     } else {
-      const float hn = (r10 * (tanhf(c) * o + l10 / r10)) / r10;
+      const float hn = div_rn(r10 * (tanhf(c) * o + l10r), r10, k.ir10);
       p.gate[4][idx] = c;
       p.gate[5][idx] = hn;
       l_store_h_side(p, idx, hn);
-      l_duals_store(p, idx, d, c, hn, c_, acc);
+      l_duals_store(p, idx, d, c, hn, c_, acc, k);
     }
   }
   if (!LAST) {
@@ -372,12 +394,13 @@ __global__ void __launch_bounds__(NT) l_last_a_kernel(const float* h, const floa
 }
 __global__ void __launch_bounds__(NT) l_duals_kernel(const LSlot p) {
   const int64_t total = (int64_t)p.H * p.ldn;
+  const LRcp k(p.hp);
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int j = blockIdx.y; j < p.H; j += gridDim.y)
   for (int64_t n = (int64_t)blockIdx.x * NT + threadIdx.x; n < p.n; n += (int64_t)gridDim.x * NT) {   // ghost rows untouched
     const int64_t idx = (int64_t)j * p.ldn + n;
     const LDualIn d = l_duals_load(p, idx, total);
-    l_duals_store(p, idx, d, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx], acc);
+    l_duals_store(p, idx, d, p.gate[4][idx], p.gate[5][idx], p.c_prev[idx], acc, k);
   }
   track_bound(p.bound_track, acc[4]);
 #pragma unroll

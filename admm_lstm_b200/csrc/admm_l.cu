@@ -229,7 +229,7 @@ __device__ __forceinline__ float l_update_z(float z, float out, float P, float l
 }
 
 // z_f,f, z_i,i, z_o,o, z_g,g (main.py:150-165) + the reductions update_c needs
-__global__ void __launch_bounds__(NT) l_gates_kernel(const LSlot p, float* red_max, double* red_sum) {
+__global__ void __launch_bounds__(NT, 4) l_gates_kernel(const LSlot p, float* red_max, double* red_sum) {
   __shared__ float red[NT / 32];
   __shared__ double redd[NT / 32];
   const int64_t total = (int64_t)p.H * p.ldn;
@@ -417,7 +417,32 @@ dim3 ew_grid2(int64_t ldn, int rows) {
   return dim3((unsigned)gx, (unsigned)gy);
 }
 
-// the same with one sample per thread
+// The gate pass (33 one-float streams per element, bound by memory latency) runs ONE resident wave instead: SMs x the CTAs
+// that fit on an SM (64 registers under __launch_bounds__(NT, 4): 4, not the 8 the fixed grids assume -- 1216 CTAs on 444
+// slots were 2.74 waves of long-running CTAs), x over sample blocks (the kernel strides over them), y over rows: 52.5 ->
+// 45.4 ms per iteration at the configs[4] shape (same-box A/B).  The cell and packing passes measured 3-4 % SLOWER with
+// one resident wave of 3 CTAs per SM and keep the fixed grid.
+dim3 ew_grid_resident(const void* kernel, int64_t n_blocks, int rows) {
+  static const void* known[8];
+  static int occ_of[8];
+  static int n_known = 0;
+  int occ = 0;
+  for (int i = 0; i < n_known; ++i)
+    if (known[i] == kernel) occ = occ_of[i];
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NT, 0) != cudaSuccess || occ < 1) occ = 2;
+    if (n_known < 8) { known[n_known] = kernel; occ_of[n_known++] = occ; }
+  }
+  const int64_t slots = 148LL * occ;
+  int64_t gx = n_blocks < slots ? n_blocks : slots;
+  if (gx < 1) gx = 1;
+  int64_t gy = slots / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  return dim3((unsigned)gx, (unsigned)gy);
+}
+
+// 2-D grid of ~148*8 CTAs for the light kernels: x over the samples (one per thread), y over rows
 dim3 ew_grid1(int64_t ldn, int rows) {
   const int64_t gx = (ldn + NT - 1) / NT;
   int64_t gy = (148 * 8 + gx - 1) / gx;
@@ -596,7 +621,7 @@ int admm_l_sweep_gates(const admm_l_problem* lp, int s, float* scratch, float* r
   if ((rc = gemm_P(lp, s, scratch, st))) return rc;
   const LSlot k = make_slot(lp, s, scratch);
   KernelScope ks_("l_gates_kernel", st);
-  l_gates_kernel<<<ew_grid1(k.ldn, k.H), NT, 0, st>>>(k, red_max, red_sum);
+  l_gates_kernel<<<ew_grid_resident((const void*)l_gates_kernel, (k.ldn + NT - 1) / NT, k.H), NT, 0, st>>>(k, red_max, red_sum);
   count_launch();
   return check_launch("l_gates");
 }

@@ -255,3 +255,66 @@ def test_fused_moment_accumulation_equals_coefficient_form(is_g):
         assert abs(out[k] - exact) <= 2e-7 * scale, (k, out[k], exact)           # first form
         assert abs(out[4 + k] - exact) <= 2e-7 * scale, (k, out[4 + k], exact)   # fused form
         assert abs(out[4 + k] - out[k]) <= 2e-7 * scale
+
+
+def _plan_ok(entry):
+    """The constraints capi.cu:check_plan puts on one pass of the probe schedule."""
+    from admm_lstm_b200 import _lib
+    k0, ncand, proof, moments = entry[:4]
+    assert (0 if moments else 1) <= ncand <= _lib.ADMM_MAX_CAND, entry
+    for k in k0:
+        assert k >= 0 and k + (0 if moments else ncand) <= _lib.ADMM_EST_CAND, entry
+        if proof:
+            assert k + (ncand if moments else 0) <= _lib.ADMM_MAX_CAND, entry
+    if len(entry) > 4:
+        assert entry[4] in (4, 6), entry
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("fused", [False, True])
+def test_probe_schedule_is_always_a_valid_plan(fused, graph):
+    """optimizer._probe_plans (host side of admm.py:331-338): for ANY max|Q| hint -- tiny, huge, inf, NaN, absent -- every pass
+    it schedules satisfies check_plan, the moment pass comes first while its window fits, a diverging run goes straight to the
+    exact passes, and the schedule always ends with the two exact 32-candidate passes that decide whatever is left."""
+    import types
+    from admm_lstm_b200 import _lib
+    from admm_lstm_b200.optimizer import ADMMBasedOptimizer
+    full = [((0, 0, 0, 0), _lib.ADMM_MAX_CAND, 0, 0), ((32, 32, 32, 32), _lib.ADMM_MAX_CAND, 0, 0)]
+    stub = types.SimpleNamespace(probe="moments", _hint=None, _hint_q=None, uses_tensor_cores=fused,
+                                 _zstore=object() if fused else None, moment_order=4, use_cuda_graph=graph)
+    plans = ADMMBasedOptimizer._probe_plans(stub, _lib.SRC_X)
+    assert plans[1:] == full and plans[0][0] == (0, 0, 0, 0) and plans[0][3] == 1          # no hint yet: expansion from k0 = 0
+    order = 4 if fused else 6
+    qs = [0.0, 1e-30, 2.0 ** -9, 2.0 ** -7, 2.0 ** -5, 0.1, 0.4, 1.0, 180.0, 1e5, 2.0 ** 22, 2.0 ** 23, 2.0 ** 24, 1e9, 1e30,
+          float("inf"), float("nan")]
+    for q in qs:
+        for src in (_lib.SRC_X, _lib.SRC_H):
+            stub._hint_q = {_lib.SRC_X: [q, 0.01, q / 3 if q == q else q, 0.2], _lib.SRC_H: [0.3, q, 0.05, q]}
+            plans = ADMMBasedOptimizer._probe_plans(stub, src)
+            for entry in plans:
+                _plan_ok(entry)
+            assert plans[-2:] == full
+            if len(plans) == 3:
+                k0, ncand, proof, moments, o = plans[0]
+                assert moments == 1 and proof == 1 and ncand == 2 and o == order
+                lim = 2.0 ** -7 if order == 4 else 2.0 ** -5
+                for g, qg in enumerate(stub._hint_q[src]):
+                    if qg == qg and not graph:
+                        assert qg * 2.0 ** -k0[g] <= lim * (1 + 1e-6) or k0[g] == 0 and qg <= lim, (qg, k0)
+                        assert k0[g] == 0 or qg * 2.0 ** -(k0[g] - 1) > lim                # the FIRST valid exponent
+                if graph:
+                    assert len(set(k0)) == 1 and k0[0] % 2 == 0
+            else:
+                assert plans == full and not (q == q and q < 2.0 ** (_lib.ADMM_MAX_CAND - 9))   # only a diverging run skips it
+    # candidate-by-candidate mode: a window around the exits of step s-2, proofs below it
+    stub.probe, stub._hint = "exact", None
+    assert ADMMBasedOptimizer._probe_plans(stub, _lib.SRC_X) == full
+    for ks in ([0, 1, 5, 14], [31, 32, 40, 63], [14, 14, 18, 14]):
+        stub._hint = {_lib.SRC_X: ks, _lib.SRC_H: ks}
+        plans = ADMMBasedOptimizer._probe_plans(stub, _lib.SRC_H)
+        for entry in plans:
+            _plan_ok(entry)
+        k0, ncand = plans[0][0], plans[0][1]
+        assert plans[1:] == full and ncand % 8 == 0
+        for k, a in zip(ks, k0):
+            assert a <= max(0, k - 5) and (a + ncand > k + 2 or ncand == _lib.ADMM_MAX_CAND)   # the exit of s-2 and two above it

@@ -36,6 +36,8 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--dump", default="", help="write the reference's weights, gates and duals after the last step to this .npz "
+                    "(tests/test_oracle_live_reference.py; not for admm_l)")
     a = ap.parse_args()
     if not os.path.exists(os.path.join(REF, "admm.py")):
         print(json.dumps({"unavailable": "oracle/_ref is not staged (run python oracle/make_ref.py where /root/reference exists)"}))
@@ -44,6 +46,7 @@ def main() -> int:
         for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
             os.environ[k] = str(a.threads)
     data_path = os.path.abspath(a.data)
+    dump_path = os.path.abspath(a.dump) if a.dump else ""
     os.chdir(tempfile.mkdtemp(prefix="admm_ref_run_"))
     sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != os.path.dirname(HERE)]
     sys.path.insert(0, REF)
@@ -104,6 +107,11 @@ def main() -> int:
             sync()
             if s >= a.warmup:
                 times.append(time.perf_counter() - t0)
+        if a.dump:
+            rec = {f"w_{k}": getattr(model, k).detach().cpu().numpy() for k in [f"{s}2{g}" for g in "ifgo" for s in "xh"] + ["out"]}
+            rec.update({f"gate_{k}": v.detach().cpu().numpy() for k, v in opt.gates.items()})
+            rec.update({f"dual_{k}": v.detach().cpu().numpy() for k, v in opt.duals.items()})
+            np.savez(dump_path, **rec)
     out = {"step_s": times, "threads": int(torch.get_num_threads()), "device": str(dev), "torch": torch.__version__,
            "n": int(d["x"].shape[0])}
     if dev.type == "cuda":

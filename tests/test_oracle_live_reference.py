@@ -51,3 +51,34 @@ def test_oracle_equals_live_reference(variant, params, shape, seed, cls, tmp_pat
     for k in ("i", "f", "g", "o", "c"):
         scale = max(float(np.abs(ref[f"dual_{k}"]).max()), float(params["rho"][k]))
         assert float(np.abs(ora.duals[k] - ref[f"dual_{k}"]).max()) <= 1e-4 * scale, k
+
+
+@pytest.mark.parametrize("shape,hidden,iters,seed", [((31, 4, 2), 5, 3, 201), ((53, 2, 6), 12, 3, 202)])
+def test_l_oracle_equals_live_reference_functions(shape, hidden, iters, seed):
+    """ADMM-LSTM-L: oracle/admm_l_oracle.py against the reference's own update functions (oracle/_ref/comparison_experiment/
+    admm_l/admm_lstm.py, pure torch) driven live in the order of main.py:139-191 by tests/golden/make_golden_l.py's loop, on
+    problems that are not among the fixtures."""
+    import importlib.util
+    import torch
+    from test_oracle_l_golden import check_state, make_oracle, rel
+    from oracle.admm_l_oracle import GATES
+    ref_file = os.path.join(REF, "comparison_experiment", "admm_l", "admm_lstm.py")
+    if not os.path.exists(ref_file):
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py needs /root/reference)")
+    spec = importlib.util.spec_from_file_location("make_golden_l_live", os.path.join(ROOT, "tests", "golden", "make_golden_l.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gen.REF = ref_file
+    ref = gen.load_ref()
+    torch.manual_seed(seed)
+    x, y = torch.rand(*shape), torch.rand(shape[0], 1)
+    d = gen.run_case(ref, x, y, None, None, hidden, iters, seed=seed + 1000)
+    o = make_oracle(d)
+    for k in range(1, iters + 1):
+        o.step()
+        for g in GATES:
+            assert rel(o.W[g], d[f"it{k}_W{g}"]) < 1e-5, (k, g)
+            assert rel(o.U[g], d[f"it{k}_U{g}"]) < 1e-5, (k, g)
+        assert rel(o.Wy, d[f"it{k}_Wy"]) < 1e-5
+        check_state(o, d, k)
+        assert abs(o.loss() - d["train_loss"][k]) < 1e-5 * max(1.0, d["train_loss"][k])
